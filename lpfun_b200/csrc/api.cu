@@ -1,0 +1,556 @@
+// C ABI of liblpfnt.so: plan management, operator dispatch, host<->device staging.
+// See include/lpfnt.h for the contract of every entry point and the reference call sites
+// (src/lpfun/transform.py, src/lpfun/core/molecules.py) each one replaces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "eval_launch.h"
+#include "lpfnt_internal.h"
+#include "sweep_launch.h"
+
+using namespace lpfnt;
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+            return LPFNT_ECUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+namespace {
+
+struct DeviceDim {
+    int32_t *thr_fib = nullptr, *thr_start = nullptr, *fib_ptr = nullptr;
+    int2 *ent = nullptr;
+    int32_t num_threads = 0, max_lines = 0;
+};
+
+int tri_size(int n1) { return n1 * (n1 + 1) / 2; }
+
+}  // namespace
+
+struct lpfnt_plan {
+    int device = 0;
+    int m = 0, n = 0;
+    int64_t N = 0, N1 = 0;
+    int max_line = 0;
+    bool has_perm = false;
+    // device tables
+    int32_t *d_line_off = nullptr, *d_perm = nullptr;
+    uint8_t *d_line_alpha = nullptr;
+    int64_t *d_A = nullptr;       // only for the generic eval fallback (uploaded lazily)
+    double *d_nodes = nullptr, *d_mat = nullptr;  // generic-kernel matrix scratch
+    DeviceDim dd[kMaxDim + 1];
+    std::vector<int64_t> hA;      // kept only when the generic eval may need it
+    // host copies of the 1-D operators (reference packing)
+    std::vector<double> nodes, Vx_lt, inv_Vx_lt, Dx_ut[3], DxT_lt[3];
+    // workspaces (grown on demand)
+    double *ws[3] = {nullptr, nullptr, nullptr};
+    size_t ws_bytes[3] = {0, 0, 0};
+    cudaStream_t stream = nullptr;  // used by the host-pointer paths
+    int64_t launches = 0;
+    int64_t table_bytes = 0;
+    int force_generic = 0;
+    // optional per-launch tracing (CUDA events around every kernel launch)
+    int trace = 0;
+    struct TraceRec { int label; cudaEvent_t a, b; };
+    std::vector<TraceRec> trace_recs;
+};
+
+namespace {
+
+template <typename T>
+int upload(T **dst, const T *src, size_t count, lpfnt_plan *p) {
+    *dst = nullptr;
+    if (count == 0) return LPFNT_OK;
+    CK(cudaMalloc(reinterpret_cast<void **>(dst), count * sizeof(T)));
+    CK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    p->table_bytes += int64_t(count * sizeof(T));
+    return LPFNT_OK;
+}
+
+int ensure_ws(lpfnt_plan *p, int slot, size_t bytes) {
+    if (p->ws_bytes[slot] >= bytes) return LPFNT_OK;
+    if (p->ws[slot]) CK(cudaFree(p->ws[slot]));
+    p->ws[slot] = nullptr;
+    p->ws_bytes[slot] = 0;
+    CK(cudaMalloc(reinterpret_cast<void **>(&p->ws[slot]), bytes));
+    p->ws_bytes[slot] = bytes;
+    return LPFNT_OK;
+}
+
+
+// Tracing: label = 100 * kernel kind (0 line sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4 fused tile) + coordinate.
+void trace_begin(lpfnt_plan *p, int label, cudaStream_t s) {
+    if (!p->trace) return;
+    lpfnt_plan::TraceRec r{label, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    p->trace_recs.push_back(r);
+}
+void trace_end(lpfnt_plan *p, cudaStream_t s) {
+    if (!p->trace || p->trace_recs.empty()) return;
+    cudaEventRecord(p->trace_recs.back().b, s);
+}
+
+// Re-pack a reference-layout triangle of size n1 into the kernels' compile-time layout of
+// capacity cap (see PackedTri): lower stays row-major, upper becomes its transposed lower form.
+void repack(const double *src, int n1, int kind, int cap, std::vector<double> &dst) {
+    dst.assign(tri_size(cap), 0.0);
+    if (kind == LPFNT_LOWER) {
+        std::copy(src, src + tri_size(n1), dst.begin());
+    } else {
+        for (int k = 0; k < n1; ++k) {
+            const double *row = src + int64_t(k) * n1 - int64_t(k) * (k - 1) / 2;
+            for (int j = k; j < n1; ++j) dst[j * (j + 1) / 2 + k] = row[j - k];
+        }
+    }
+    // unit diagonal beyond n1 keeps the (never executed) padded solve rows finite
+    for (int k = n1; k < cap; ++k) dst[k * (k + 1) / 2 + k] = 1.0;
+}
+
+int pick_cap(int len) {
+    if (len <= 8) return 8;
+    if (len <= 16) return 16;
+    if (len <= 24) return 24;
+    if (len <= 32) return 32;
+    return 0;
+}
+
+struct SweepSpec {
+    const double *packed;  // host, reference packing
+    int kind;              // LPFNT_LOWER / LPFNT_UPPER
+    bool solve;
+    bool fma;
+};
+
+int sweep_mode(const SweepSpec &s) {
+    if (s.kind == LPFNT_LOWER) return s.solve ? kLowerSolve : kLowerMatvec;
+    return s.solve ? kUpperSolve : kUpperMatvec;
+}
+
+// One sweep along coordinate h: src -> dst (device pointers, may alias when no perm is used).
+int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, const double *src, double *dst, int64_t batch,
+               bool gather, bool scatter, cudaStream_t s) {
+    const int n1 = p->n + 1;
+    const int mode = sweep_mode(spec);
+    const int len = (h == 0) ? p->max_line : p->dd[h].max_lines;
+    const int cap = p->force_generic ? 0 : pick_cap(std::max(len, 1));
+    std::vector<double> tri;
+    if (cap) repack(spec.packed, n1, spec.kind, cap, tri);
+    else {
+        // generic kernel reads the matrix from device memory (stream ordered copy of a small table)
+        CK(cudaMemcpyAsync(p->d_mat, spec.packed, sizeof(double) * tri_size(n1), cudaMemcpyHostToDevice, s));
+    }
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = int(std::min<int64_t>(65535, batch - b0));
+        const double *in = src + b0 * p->N;
+        double *out = dst + b0 * p->N;
+        cudaError_t e = cudaSuccess;
+        trace_begin(p, (cap == 0 ? 200 : (h == 0 ? 0 : 100)) + h, s);
+        if (cap == 0) {
+            GenericArgs a{};
+            a.in = in; a.out = out; a.mat = p->d_mat; a.line_off = p->d_line_off;
+            a.perm_in = gather ? p->d_perm : nullptr;
+            a.perm_out = scatter ? p->d_perm : nullptr;
+            a.stride = p->N; a.n1 = n1; a.mode = mode; a.fma = spec.fma ? 1 : 0;
+            if (h == 0) { a.ent = nullptr; a.num_threads = int32_t(p->N1); }
+            else {
+                const DeviceDim &d = p->dd[h];
+                a.thr_fib = d.thr_fib; a.thr_start = d.thr_start; a.fib_ptr = d.fib_ptr; a.ent = d.ent;
+                a.num_threads = d.num_threads;
+            }
+            e = launch_generic_sweep(a, nb, s);
+        } else if (h == 0) {
+            LineSweepArgs a{in, out, p->d_line_off, gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, int32_t(p->N1)};
+            switch (cap) {
+                case 8: e = launch_line_sweep<8>(mode, spec.fma, a, tri.data(), nb, s); break;
+                case 16: e = launch_line_sweep<16>(mode, spec.fma, a, tri.data(), nb, s); break;
+                case 24: e = launch_line_sweep<24>(mode, spec.fma, a, tri.data(), nb, s); break;
+                default: e = launch_line_sweep<32>(mode, spec.fma, a, tri.data(), nb, s); break;
+            }
+        } else {
+            if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
+            const DeviceDim &d = p->dd[h];
+            FibreSweepArgs a{in, out, d.thr_fib, d.thr_start, d.fib_ptr, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_threads};
+            switch (cap) {
+                case 8: e = launch_fibre_sweep<8>(mode, spec.fma, a, tri.data(), nb, s); break;
+                case 16: e = launch_fibre_sweep<16>(mode, spec.fma, a, tri.data(), nb, s); break;
+                case 24: e = launch_fibre_sweep<24>(mode, spec.fma, a, tri.data(), nb, s); break;
+                default: e = launch_fibre_sweep<32>(mode, spec.fma, a, tri.data(), nb, s); break;
+            }
+        }
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    }
+    return LPFNT_OK;
+}
+
+// Device-resident pipeline: sweeps along `dims` (ascending), optional colex gather on the way
+// in and scatter on the way out.  in/out may alias.
+int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
+               int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+    gather = gather && p->has_perm;
+    scatter = scatter && p->has_perm;
+    const size_t bytes = size_t(batch) * size_t(p->N) * sizeof(double);
+    const int nd = int(dims.size());
+    if (nd == 0) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
+    if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
+    if (!gather && !scatter) {
+        for (int q = 0; q < nd; ++q) {
+            int rc = launch_dim(p, spec, dims[q], q == 0 ? in : out, out, batch, false, false, s);
+            if (rc) return rc;
+        }
+        return LPFNT_OK;
+    }
+    // with a permutation the permuting sweep must not run in place
+    if (nd == 1) {
+        double *dst = out;
+        if (in == out) { int rc = ensure_ws(p, 2, bytes); if (rc) return rc; dst = p->ws[2]; }
+        int rc = launch_dim(p, spec, dims[0], in, dst, batch, gather, scatter, s);
+        if (rc) return rc;
+        if (dst != out) CK(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToDevice, s));
+        return LPFNT_OK;
+    }
+    // first sweep: in -> mid ; middle sweeps in place on mid ; last sweep: mid -> out
+    double *mid = out;
+    if (scatter || in == out) { int rc = ensure_ws(p, 2, bytes); if (rc) return rc; mid = p->ws[2]; }
+    for (int q = 0; q < nd; ++q) {
+        const bool first = (q == 0), last = (q == nd - 1);
+        int rc = launch_dim(p, spec, dims[q], first ? in : mid, last ? out : mid, batch, first && gather, last && scatter, s);
+        if (rc) return rc;
+    }
+    return LPFNT_OK;
+}
+
+// Host-pointer front end: stage through ws[0]/ws[1] in chunks of functions.
+int run_any(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
+            int64_t batch, bool gather, bool scatter, int on_device, void *stream) {
+    if (!p || !in || !out || batch < 1) { set_error("null pointer or empty batch"); return LPFNT_EINVAL; }
+    if (!spec.packed) { set_error("the plan was created without the matrix this operation needs"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(p->device));
+    if (on_device) return run_device(p, spec, dims, in, out, batch, gather, scatter, static_cast<cudaStream_t>(stream));
+    const size_t fbytes = size_t(p->N) * sizeof(double);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, int64_t((size_t(512) << 20) / fbytes)));
+    int rc = ensure_ws(p, 0, size_t(chunk) * fbytes);
+    if (rc) return rc;
+    rc = ensure_ws(p, 1, size_t(chunk) * fbytes);
+    if (rc) return rc;
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+        const int64_t nb = std::min(chunk, batch - b0);
+        CK(cudaMemcpyAsync(p->ws[0], in + b0 * p->N, size_t(nb) * fbytes, cudaMemcpyHostToDevice, p->stream));
+        rc = run_device(p, spec, dims, p->ws[0], p->ws[1], nb, gather, scatter, p->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out + b0 * p->N, p->ws[1], size_t(nb) * fbytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return LPFNT_OK;
+}
+
+std::vector<int> all_dims(int m) {
+    std::vector<int> d(m);
+    for (int i = 0; i < m; ++i) d[i] = i;
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lpfnt_version(void) { return "lpfnt-b200 0.1.0 (sm_100a)"; }
+
+int lpfnt_device_count(int *count) {
+    if (!count) { set_error("null pointer"); return LPFNT_EINVAL; }
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    return LPFNT_OK;
+}
+
+int lpfnt_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) { set_error("bad arguments"); return LPFNT_EINVAL; }
+    CK(cudaHostAlloc(ptr, size_t(std::max<int64_t>(bytes, 1)), cudaHostAllocPortable));
+    return LPFNT_OK;
+}
+int lpfnt_host_free(void *ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return LPFNT_OK;
+}
+
+int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *perm, const double *nodes,
+                      const double *Vx_lt, const double *inv_Vx_lt, const double *const *Dx_ut,
+                      const double *const *DxT_lt, int device, lpfnt_plan **plan) {
+    if (!plan) { set_error("plan pointer is null"); return LPFNT_EINVAL; }
+    *plan = nullptr;
+    if (!A || m < 1 || n < 0 || N < 1) { set_error("plan_create: need A, m >= 1, n >= 0, N >= 1"); return LPFNT_EINVAL; }
+    if (m > kMaxDim) { set_error("plan_create: spatial dimension above the supported maximum (12)"); return LPFNT_EUNSUPPORTED; }
+    HostIndex hx;
+    if (!hx.build(A, N, m, n)) return LPFNT_EINVAL;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("plan_create: no such CUDA device"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(device));
+
+    lpfnt_plan *p = new lpfnt_plan();
+    p->device = device; p->m = m; p->n = n; p->N = N; p->N1 = hx.N1; p->max_line = hx.max_line;
+    const int ts = tri_size(n + 1);
+    if (nodes) p->nodes.assign(nodes, nodes + n + 1);
+    if (Vx_lt) p->Vx_lt.assign(Vx_lt, Vx_lt + ts);
+    if (inv_Vx_lt) p->inv_Vx_lt.assign(inv_Vx_lt, inv_Vx_lt + ts);
+    for (int k = 0; k < 3; ++k) {
+        if (Dx_ut && Dx_ut[k]) p->Dx_ut[k].assign(Dx_ut[k], Dx_ut[k] + ts);
+        if (DxT_lt && DxT_lt[k]) p->DxT_lt[k].assign(DxT_lt[k], DxT_lt[k] + ts);
+    }
+    int rc = LPFNT_OK;
+    auto fail = [&](int code) { lpfnt_plan_destroy(p); return code; };
+    if ((rc = upload(&p->d_line_off, hx.line_off.data(), hx.line_off.size(), p))) return fail(rc);
+    if (perm) {
+        std::vector<int32_t> p32(N);
+        std::vector<uint8_t> seen(N, 0);
+        for (int64_t i = 0; i < N; ++i) {
+            if (perm[i] < 0 || perm[i] >= N || seen[perm[i]]) { set_error("plan_create: perm is not a permutation of 0..N-1"); return fail(LPFNT_EINVAL); }
+            seen[perm[i]] = 1;
+            p32[i] = int32_t(perm[i]);
+        }
+        if ((rc = upload(&p->d_perm, p32.data(), p32.size(), p))) return fail(rc);
+        p->has_perm = true;
+    }
+    for (int h = 1; h < m; ++h) {
+        const DimTable &D = hx.dims[h];
+        DeviceDim &d = p->dd[h];
+        d.num_threads = int32_t(D.num_threads);
+        d.max_lines = D.max_lines;
+        if ((rc = upload(&d.thr_fib, D.thr_fib.data(), D.thr_fib.size(), p))) return fail(rc);
+        if ((rc = upload(&d.thr_start, D.thr_start.data(), D.thr_start.size(), p))) return fail(rc);
+        if ((rc = upload(&d.fib_ptr, D.fib_ptr.data(), D.fib_ptr.size(), p))) return fail(rc);
+        static_assert(sizeof(FibEnt) == sizeof(int2), "FibEnt must match int2");
+        if ((rc = upload(&d.ent, reinterpret_cast<const int2 *>(D.ent.data()), D.ent.size(), p))) return fail(rc);
+    }
+    if (!hx.line_alpha.empty())
+        if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
+    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255) p->hA.assign(A, A + N * m);  // generic eval needs A
+    if (nodes && (rc = upload(&p->d_nodes, nodes, size_t(n + 1), p))) return fail(rc);
+    {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_mat), sizeof(double) * ts);
+        if (e != cudaSuccess) { set_error("cudaMalloc(d_mat) failed"); return fail(LPFNT_ENOMEM); }
+        p->table_bytes += sizeof(double) * ts;
+    }
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(LPFNT_ECUDA); }
+    }
+    *plan = p;
+    return LPFNT_OK;
+}
+
+int lpfnt_plan_destroy(lpfnt_plan *p) {
+    if (!p) return LPFNT_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
+    cudaFree(p->d_nodes); cudaFree(p->d_mat);
+    for (int h = 0; h <= kMaxDim; ++h) {
+        cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
+    }
+    for (int s = 0; s < 3; ++s) cudaFree(p->ws[s]);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return LPFNT_OK;
+}
+
+int64_t lpfnt_plan_device_bytes(const lpfnt_plan *p) {
+    if (!p) return 0;
+    return p->table_bytes + int64_t(p->ws_bytes[0] + p->ws_bytes[1] + p->ws_bytes[2]);
+}
+int64_t lpfnt_plan_launch_count(const lpfnt_plan *p) { return p ? p->launches : 0; }
+
+int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
+    if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
+    if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    set_error(std::string("unknown option: ") + name);
+    return LPFNT_EINVAL;
+}
+
+int lpfnt_plan_trace_read(lpfnt_plan *p, int max_records, int *labels, float *ms, int *count) {
+    if (!p || !count) { set_error("bad arguments"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(p->device));
+    int n = 0;
+    for (auto &r : p->trace_recs) {
+        if (r.b) {
+            CK(cudaEventSynchronize(r.b));
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, r.a, r.b));
+            if (n < max_records && labels && ms) { labels[n] = r.label; ms[n] = t; }
+            ++n;
+        }
+        cudaEventDestroy(r.a);
+        if (r.b) cudaEventDestroy(r.b);
+    }
+    p->trace_recs.clear();
+    *count = n;
+    return LPFNT_OK;
+}
+
+int lpfnt_itransform(lpfnt_plan *p, const double *packed, int kind, int arith, const double *in, double *out,
+                     int64_t batch, int gather_perm, int scatter_perm, int on_device, void *stream) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (kind != LPFNT_LOWER && kind != LPFNT_UPPER) { set_error("kind must be LPFNT_LOWER or LPFNT_UPPER"); return LPFNT_EINVAL; }
+    SweepSpec spec{packed, kind, false, arith == LPFNT_ARITH_FMA};
+    return run_any(p, spec, all_dims(p->m), in, out, batch, gather_perm != 0, scatter_perm != 0, on_device, stream);
+}
+
+int lpfnt_transform(lpfnt_plan *p, const double *packed, int kind, const double *in, double *out, int64_t batch,
+                    int gather_perm, int scatter_perm, int on_device, void *stream) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (kind != LPFNT_LOWER) { set_error("transform: only the lower (Newton) solve is implemented"); return LPFNT_EUNSUPPORTED; }
+    SweepSpec spec{packed, kind, true, false};
+    return run_any(p, spec, all_dims(p->m), in, out, batch, gather_perm != 0, scatter_perm != 0, on_device, stream);
+}
+
+int lpfnt_dtransform(lpfnt_plan *p, const double *packed, int kind, int arith, int i, const double *in, double *out,
+                     int64_t batch, int on_device, void *stream) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (i < 0 || i >= p->m) {  // molecules.py:279-280
+        set_error("Choose a coordinate between i=0 and i=" + std::to_string(p->m - 1) + ".");
+        return LPFNT_EINVAL;
+    }
+    if (kind != LPFNT_LOWER && kind != LPFNT_UPPER) { set_error("kind must be LPFNT_LOWER or LPFNT_UPPER"); return LPFNT_EINVAL; }
+    SweepSpec spec{packed, kind, false, arith == LPFNT_ARITH_FMA};
+    return run_any(p, spec, std::vector<int>{i}, in, out, batch, false, false, on_device, stream);
+}
+
+int lpfnt_fnt(lpfnt_plan *p, const double *in, double *out, int64_t batch, int on_device, void *stream) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (!p->inv_Vx_lt.empty()) {
+        SweepSpec spec{p->inv_Vx_lt.data(), LPFNT_LOWER, false, false};
+        return run_any(p, spec, all_dims(p->m), in, out, batch, true, false, on_device, stream);
+    }
+    SweepSpec spec{p->Vx_lt.empty() ? nullptr : p->Vx_lt.data(), LPFNT_LOWER, true, false};
+    return run_any(p, spec, all_dims(p->m), in, out, batch, true, false, on_device, stream);
+}
+
+int lpfnt_ifnt(lpfnt_plan *p, const double *in, double *out, int64_t batch, int arith, int on_device, void *stream) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    SweepSpec spec{p->Vx_lt.empty() ? nullptr : p->Vx_lt.data(), LPFNT_LOWER, false, arith == LPFNT_ARITH_FMA};
+    return run_any(p, spec, all_dims(p->m), in, out, batch, false, true, on_device, stream);
+}
+
+static int check_ik(lpfnt_plan *p, int i, int k) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (i < 0 || i >= p->m) { set_error("Choose a coordinate between i=0 and i=" + std::to_string(p->m - 1) + "."); return LPFNT_EINVAL; }
+    if (k < 1 || k > 3) { set_error("Invalid value for k. Please choose 1, 2 or 3."); return LPFNT_EINVAL; }
+    return LPFNT_OK;
+}
+
+int lpfnt_dx(lpfnt_plan *p, const double *in, double *out, int i, int k, int64_t batch, int on_device, void *stream) {
+    int rc = check_ik(p, i, k);
+    if (rc) return rc;
+    SweepSpec spec{p->Dx_ut[k - 1].empty() ? nullptr : p->Dx_ut[k - 1].data(), LPFNT_UPPER, false, false};
+    return run_any(p, spec, std::vector<int>{i}, in, out, batch, false, false, on_device, stream);
+}
+
+int lpfnt_dxT(lpfnt_plan *p, const double *in, double *out, int i, int k, int64_t batch, int on_device, void *stream) {
+    int rc = check_ik(p, i, k);
+    if (rc) return rc;
+    SweepSpec spec{p->DxT_lt[k - 1].empty() ? nullptr : p->DxT_lt[k - 1].data(), LPFNT_LOWER, false, false};
+    return run_any(p, spec, std::vector<int>{i}, in, out, batch, false, false, on_device, stream);
+}
+
+int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points, int64_t P, double *values,
+                       int on_device, void *stream) {
+    if (!p || !coeffs || !values || P < 0 || (P > 0 && !points)) { set_error("eval: bad arguments"); return LPFNT_EINVAL; }
+    if (p->nodes.empty()) { set_error("eval: the plan was created without nodes"); return LPFNT_EINVAL; }
+    if (P == 0) return LPFNT_OK;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t s = on_device ? static_cast<cudaStream_t>(stream) : p->stream;
+    const double *dc = coeffs, *dp = points;
+    double *dv = values;
+    const bool fast = !p->force_generic && (p->n + 1 <= kMaxRegT) && p->m <= kEvalMaxM && p->n <= 255 && (p->m == 1 || p->d_line_alpha);
+    const size_t cb = size_t(p->N) * sizeof(double), pb = size_t(P) * p->m * sizeof(double), vb = size_t(P) * sizeof(double);
+    if (!on_device) {
+        int rc = ensure_ws(p, 0, cb + pb);
+        if (rc) return rc;
+        rc = ensure_ws(p, 1, vb);
+        if (rc) return rc;
+        double *w = p->ws[0];
+        CK(cudaMemcpyAsync(w, coeffs, cb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w + p->N, points, pb, cudaMemcpyHostToDevice, s));
+        dc = w; dp = w + p->N; dv = p->ws[1];
+    }
+    if (fast) {
+        // grid.x is 32-bit: chunk very large point sets
+        const int64_t step = int64_t(1) << 30;
+        for (int64_t q0 = 0; q0 < P; q0 += step) {
+            const int64_t np = std::min(step, P - q0);
+            EvalArgs a{dc, dp + q0 * p->m, dv + q0, p->d_line_off, p->d_line_alpha, np, int32_t(p->N1), p->m};
+            trace_begin(p, 300, s);
+            cudaError_t e = launch_eval_horner(a, p->nodes.data(), p->n + 1, s);
+            trace_end(p, s);
+            p->launches += 1;
+            if (e != cudaSuccess) { set_error(std::string("eval launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+        }
+    } else {
+        if (!p->d_A) {
+            if (p->hA.empty()) { set_error("eval: generic path needs the multi-index array"); return LPFNT_EUNSUPPORTED; }
+            int rc = upload(&p->d_A, p->hA.data(), p->hA.size(), p);
+            if (rc) return rc;
+        }
+        const int64_t per_point = int64_t(p->m) * (p->n + 1);
+        const int64_t step = std::max<int64_t>(128, (int64_t(256) << 20) / (per_point * 8));
+        int rc = ensure_ws(p, 2, size_t(std::min(step, P)) * per_point * sizeof(double));
+        if (rc) return rc;
+        for (int64_t q0 = 0; q0 < P; q0 += step) {
+            const int64_t np = std::min(step, P - q0);
+            EvalGenericArgs a{dc, dp + q0 * p->m, p->d_nodes, dv + q0, p->d_A, p->ws[2], np, p->N, p->m, p->n};
+            cudaError_t e = launch_eval_generic(a, s);
+            p->launches += 1;
+            if (e != cudaSuccess) { set_error(std::string("eval launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+        }
+    }
+    if (!on_device) {
+        CK(cudaMemcpyAsync(values, dv, vb, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return LPFNT_OK;
+}
+
+int lpfnt_eval(lpfnt_plan *p, const double *coeffs, const double *points, int64_t P, double *values, int on_device, void *stream) {
+    return lpfnt_newton2point(p, coeffs, points, P, values, on_device, stream);
+}
+
+int lpfnt_measure_fp64(int device, int iters, double *fma_per_s) {
+    if (!fma_per_s || iters < 1) { set_error("bad arguments"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *sink = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void **>(&sink), 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0, nullptr));
+        CK(launch_fp64_probe(sink, iters, blocks, nullptr));
+        CK(cudaEventRecord(e1, nullptr));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fmas = double(blocks) * 256.0 * 8.0 * double(iters);
+        if (rep > 0) best = std::max(best, fmas / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *fma_per_s = best;
+    return LPFNT_OK;
+}
+
+}  // extern "C"

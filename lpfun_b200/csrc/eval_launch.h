@@ -1,0 +1,10 @@
+#pragma once
+#include <cuda_runtime.h>
+
+#include "eval_kernels.cuh"
+
+namespace lpfnt {
+cudaError_t launch_eval_horner(const EvalArgs &a, const double *nodes, int n1, cudaStream_t s);
+cudaError_t launch_eval_generic(const EvalGenericArgs &a, cudaStream_t s);
+cudaError_t launch_fp64_probe(double *sink, int iters, int blocks, cudaStream_t s);
+}  // namespace lpfnt

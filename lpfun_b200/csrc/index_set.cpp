@@ -1,0 +1,387 @@
+// Host-side index structure of the l^p lower set: enumeration, line lengths, trie levels,
+// per-coordinate fibre tables.  Pure C++ (no CUDA); exported through the C ABI in include/lpfnt.h.
+//
+// Reference behaviour restated here (paths relative to the reference repository):
+//   lp_set / _lp_set      src/lpfun/core/set.py:12-74
+//   lp_tube / _lp_tube    src/lpfun/core/set.py:80-107
+//   entropy               src/lpfun/core/set.py:167-182
+//   ordinal_embedding     src/lpfun/core/set.py:208-239
+// The reference never materialises fibre tables: it either exploits the coordinate symmetry of
+// the set (2d/3d kernels), recomputes embeddings inside the loops (md kernels,
+// src/lpfun/core/atoms.py:1060-1095) or permutes the whole vector (dx, molecules.py:298-308).
+// Here the tables are built ONCE per plan from A alone, without any symmetry assumption.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "lpfnt_internal.h"
+
+namespace lpfnt {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+namespace {
+
+// Odometer over N^m in colexicographic order with the reference's membership rule.
+// The running sum of a_j^p is updated exactly like set.py:31-34/37-39 (subtract the old digit
+// power, add the new one), a failing candidate is re-tested with a freshly accumulated sum
+// (set.py:46-47) and, if it fails again, digit j is reset and the carry moves on (set.py:52-55).
+class LpOdometer {
+  public:
+    LpOdometer(int m, int n, double p) : m_(m), n_(n), p_(p), digit_(m, 0), digit_pow_(m, 0.0), pow_(n + 1) {
+        for (int k = 0; k <= n; ++k) pow_[k] = std::pow(static_cast<double>(k), p);
+        limit_ = std::pow(static_cast<double>(n), p);
+    }
+    const std::vector<int64_t> &digits() const { return digit_; }
+
+    // Moves to the next member; returns false when the enumeration is exhausted.
+    bool next() {
+        int j = 0;
+        for (;;) {
+            // increment digit j, carrying over saturated digits
+            while (true) {
+                if (j >= m_) return false;
+                drop(j);
+                if (digit_[j] < n_) {
+                    digit_[j] += 1;
+                    digit_pow_[j] = pow_[digit_[j]];
+                    sum_ = sum_ + digit_pow_[j];
+                    break;
+                }
+                digit_[j] = 0;
+                digit_pow_[j] = 0.0;
+                ++j;
+            }
+            if (sum_ <= limit_) return true;
+            sum_ = fresh_sum();
+            if (sum_ <= limit_) return true;
+            drop(j);
+            digit_[j] = 0;
+            digit_pow_[j] = 0.0;
+            ++j;
+        }
+    }
+
+  private:
+    void drop(int j) { sum_ = sum_ - digit_pow_[j]; }
+    double fresh_sum() const {
+        double s = 0.0;
+        for (int q = 0; q < m_; ++q) s += std::pow(static_cast<double>(digit_[q]), p_);
+        return s;
+    }
+    int m_, n_;
+    double p_, limit_ = 0.0, sum_ = 0.0;
+    std::vector<int64_t> digit_;
+    std::vector<double> digit_pow_, pow_;
+};
+
+int64_t ipow_checked(int64_t base, int e) {
+    int64_t r = 1;
+    for (int i = 0; i < e; ++i) {
+        if (r > (INT64_MAX / base)) return -1;
+        r *= base;
+    }
+    return r;
+}
+
+int64_t enumerate(int m, int n, double p, int64_t *A, int64_t cap) {
+    if (m == 1) {  // set.py:68-69
+        if (A) {
+            if (cap < n + 1) return -1;
+            for (int k = 0; k <= n; ++k) A[k] = k;
+        }
+        return n + 1;
+    }
+    if (std::isinf(p)) {  // set.py:70-73: full tensor grid, coordinate 0 fastest
+        int64_t N = ipow_checked(n + 1, m);
+        if (N < 0) return -1;
+        if (A) {
+            if (cap < N) return -1;
+            std::vector<int64_t> d(m, 0);
+            for (int64_t r = 0; r < N; ++r) {
+                for (int j = 0; j < m; ++j) A[r * m + j] = d[j];
+                for (int j = 0; j < m; ++j) {
+                    if (++d[j] <= n) break;
+                    d[j] = 0;
+                }
+            }
+        }
+        return N;
+    }
+    LpOdometer od(m, n, p);
+    int64_t rows = 0;
+    do {
+        if (A) {
+            if (rows >= cap) return -1;
+            std::memcpy(A + rows * m, od.digits().data(), sizeof(int64_t) * m);
+        }
+        ++rows;
+    } while (od.next());
+    return rows;
+}
+
+}  // namespace
+
+bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
+    m = m_;
+    n = n_;
+    N = N_;
+    if (m < 1 || N < 1 || n < 0) {
+        set_error("HostIndex: invalid sizes");
+        return false;
+    }
+    if (N >= (int64_t(1) << 31) - 1) {
+        set_error("HostIndex: N exceeds the 32-bit offset range of the device tables");
+        return false;
+    }
+    // ---- lines (runs of coordinate 0) ----
+    line_off.clear();
+    for (int64_t e = 0; e < N; ++e) {
+        const int64_t a0 = A[e * m];
+        if (a0 == 0) line_off.push_back(static_cast<int32_t>(e));
+        else if (a0 != e - line_off.back()) {
+            set_error("HostIndex: A is not colex ordered (coordinate 0 must count up along each line)");
+            return false;
+        }
+    }
+    N1 = static_cast<int64_t>(line_off.size());
+    line_off.push_back(static_cast<int32_t>(N));
+    max_line = 0;
+    for (int64_t l = 0; l < N1; ++l) max_line = std::max(max_line, line_off[l + 1] - line_off[l]);
+    if (max_line > n + 1) {
+        set_error("HostIndex: a line is longer than n+1");
+        return false;
+    }
+
+    // ---- trie levels: a level-k node (k = 1..m-1) is a distinct suffix (a_k..a_{m-1});
+    //      level 1 = lines.  node[k][l] = level-k ancestor of line l. ----
+    auto key = [&](int64_t l, int j) -> int64_t { return A[int64_t(line_off[l]) * m + j]; };  // a_j of line l, j >= 1
+    std::vector<std::vector<int32_t>> node(m + 1), first_child(m + 1), nchild(m + 1);
+    level_size.assign(m + 1, 1);
+    level_size[0] = N;
+    if (m >= 2) level_size[1] = N1;
+    for (int k = 2; k <= m - 1; ++k) {
+        node[k].resize(N1);
+        int32_t cur = -1;
+        for (int64_t l = 0; l < N1; ++l) {
+            bool starts = true;
+            for (int j = 1; j < k; ++j)
+                if (key(l, j) != 0) { starts = false; break; }
+            if (starts) ++cur;
+            node[k][l] = cur;
+        }
+        level_size[k] = cur + 1;
+    }
+    // first_child[k][v]: index (at level k-1) of the first child of level-k node v, k = 2..m-1
+    for (int k = 2; k <= m - 1; ++k) {
+        first_child[k].assign(level_size[k], -1);
+        nchild[k].assign(level_size[k], 0);
+        for (int64_t l = 0; l < N1; ++l) {
+            const int32_t v = node[k][l];
+            const int32_t child = (k == 2) ? static_cast<int32_t>(l) : node[k - 1][l];
+            if (first_child[k][v] < 0) first_child[k][v] = child;
+            nchild[k][v] = child - first_child[k][v] + 1;
+        }
+    }
+    // children of the root (level m) are the level-(m-1) nodes 0..level_size[m-1]-1
+
+    auto level_node = [&](int k, int64_t l) -> int32_t {  // level-k ancestor of line l (k = 1..m-1)
+        return k == 1 ? static_cast<int32_t>(l) : node[k][l];
+    };
+
+    // ---- per-coordinate fibre tables ----
+    dims.assign(m, DimTable());
+    std::vector<int32_t> nxt(N1);
+    for (int h = 1; h < m; ++h) {
+        DimTable &D = dims[h];
+        std::fill(nxt.begin(), nxt.end(), -1);
+        int32_t roots = 0;
+        for (int64_t l = 0; l < N1; ++l) {
+            const int64_t ah = key(l, h);
+            if (ah == 0) { ++roots; continue; }
+            // locate the line with a_h - 1: walk down from the level-(h+1) ancestor
+            int32_t c;
+            if (h + 1 <= m - 1) {
+                const int32_t anc = level_node(h + 1, l);
+                if (ah - 1 >= nchild[h + 1][anc]) { set_error("HostIndex: set is not downward closed"); return false; }
+                c = first_child[h + 1][anc] + static_cast<int32_t>(ah - 1);
+            } else {
+                c = static_cast<int32_t>(ah - 1);  // child of the root
+            }
+            for (int j = h - 1; j >= 1; --j) {  // c is a level-(j+1) node; descend to its child a_j
+                const int64_t aj = key(l, j);
+                if (aj >= nchild[j + 1][c]) { set_error("HostIndex: set is not downward closed"); return false; }
+                c = first_child[j + 1][c] + static_cast<int32_t>(aj);
+            }
+            // c is now a line index
+            if (c < 0 || c >= N1 || nxt[c] != -1) { set_error("HostIndex: inconsistent fibre structure"); return false; }
+            if (line_off[c + 1] - line_off[c] < line_off[l + 1] - line_off[l]) {
+                set_error("HostIndex: line lengths must not increase along a fibre");
+                return false;
+            }
+            nxt[c] = static_cast<int32_t>(l);
+        }
+        D.num_fibres = roots;
+        D.fib_ptr.assign(roots + 1, 0);
+        D.thr_start.assign(roots + 1, 0);
+        D.ent.resize(N1);
+        int32_t f = 0, pos = 0;
+        int64_t thr = 0;
+        D.max_lines = 0;
+        for (int64_t l = 0; l < N1; ++l) {
+            if (key(l, h) != 0) continue;
+            D.fib_ptr[f] = pos;
+            D.thr_start[f] = static_cast<int32_t>(thr);
+            thr += line_off[l + 1] - line_off[l];
+            int32_t cnt = 0;
+            for (int32_t q = static_cast<int32_t>(l); q >= 0; q = nxt[q]) {
+                D.ent[pos++] = FibEnt{line_off[q], line_off[q + 1] - line_off[q]};
+                ++cnt;
+            }
+            D.max_lines = std::max(D.max_lines, cnt);
+            ++f;
+        }
+        D.fib_ptr[f] = pos;
+        D.thr_start[f] = static_cast<int32_t>(thr);
+        if (pos != N1) { set_error("HostIndex: fibre tables do not cover all lines"); return false; }
+        D.num_threads = thr;
+        D.thr_fib.resize(thr);
+        for (int32_t g = 0; g < roots; ++g)
+            for (int32_t t = D.thr_start[g]; t < D.thr_start[g + 1]; ++t) D.thr_fib[t] = g;
+    }
+
+    // ---- line descriptors for eval ----
+    line_alpha.clear();
+    if (n <= 255 && m >= 2) {
+        line_alpha.resize(size_t(N1) * (m - 1));
+        for (int64_t l = 0; l < N1; ++l)
+            for (int j = 1; j < m; ++j) line_alpha[l * (m - 1) + (j - 1)] = static_cast<uint8_t>(key(l, j));
+    }
+    return true;
+}
+
+}  // namespace lpfnt
+
+// ------------------------------------------------------------------------------------------
+// C ABI: host-only entry points
+// ------------------------------------------------------------------------------------------
+using namespace lpfnt;
+
+
+struct lpfnt_index {
+    lpfnt::HostIndex hx;
+};
+
+namespace {
+// returns pointer/bytes/count of a table, or false
+bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t *bytes, int64_t *count) {
+    const HostIndex &x = ix->hx;
+    auto set = [&](const void *p, size_t elem, size_t n, int64_t cnt) { *ptr = p; *bytes = elem * n; *count = cnt; return true; };
+    if (what == LPFNT_TAB_LINE_OFF) return set(x.line_off.data(), 4, x.line_off.size(), int64_t(x.line_off.size()));
+    if (what == LPFNT_TAB_LINE_ALPHA) return set(x.line_alpha.data(), 1, x.line_alpha.size(), int64_t(x.line_alpha.size()));
+    if (what == LPFNT_TAB_LEVEL_SIZE) return set(x.level_size.data(), 8, x.level_size.size(), int64_t(x.level_size.size()));
+    if (h < 1 || h >= x.m) return false;
+    const DimTable &D = x.dims[h];
+    if (what == LPFNT_TAB_FIB_PTR) return set(D.fib_ptr.data(), 4, D.fib_ptr.size(), int64_t(D.fib_ptr.size()));
+    if (what == LPFNT_TAB_FIB_ENT) return set(D.ent.data(), 8, D.ent.size(), int64_t(2 * D.ent.size()));
+    if (what == LPFNT_TAB_THR_START) return set(D.thr_start.data(), 4, D.thr_start.size(), int64_t(D.thr_start.size()));
+    if (what == LPFNT_TAB_THR_FIB) return set(D.thr_fib.data(), 4, D.thr_fib.size(), int64_t(D.thr_fib.size()));
+    return false;
+}
+}  // namespace
+
+extern "C" {
+
+const char *lpfnt_last_error(void) { return g_err.c_str(); }
+
+int64_t lpfnt_lp_set_count(int m, int n, double p) {
+    if (m < 1 || n < 0 || !((p > 0.0 && p <= 2.0) || std::isinf(p))) {
+        set_error("lp_set: need m >= 1, n >= 0, p in (0,2] or inf");
+        return LPFNT_EINVAL;
+    }
+    int64_t N = enumerate(m, n, p, nullptr, 0);
+    if (N < 0) { set_error("lp_set: size overflow"); return LPFNT_EINVAL; }
+    return N;
+}
+
+int lpfnt_lp_set_fill(int m, int n, double p, int64_t *A, int64_t N) {
+    if (!A || m < 1 || n < 0) { set_error("lp_set_fill: bad arguments"); return LPFNT_EINVAL; }
+    int64_t got = enumerate(m, n, p, A, N);
+    if (got != N) { set_error("lp_set_fill: N does not match the set size"); return LPFNT_EINVAL; }
+    return LPFNT_OK;
+}
+
+int64_t lpfnt_lp_tube(const int64_t *A, int64_t N, int m, int64_t *T) {
+    if (!A || N < 1 || m < 1) { set_error("lp_tube: bad arguments"); return LPFNT_EINVAL; }
+    int64_t lines = 0, run = 0;
+    for (int64_t e = 0; e < N; ++e) {
+        if (A[e * m] == 0 && e > 0) {
+            if (T) T[lines] = run;
+            ++lines;
+            run = 0;
+        }
+        ++run;
+    }
+    if (T) T[lines] = run;
+    return lines + 1;
+}
+
+int lpfnt_entropy(const int64_t *A, int64_t N, int m, int64_t *e_T) {
+    if (!A || !e_T || N < 1 || m < 1) { set_error("entropy: bad arguments"); return LPFNT_EINVAL; }
+    // level k size = number of members whose first k coordinates vanish
+    std::vector<int64_t> cnt(m + 1, 0);
+    for (int64_t e = 0; e < N; ++e) {
+        int z = 0;
+        while (z < m && A[e * m + z] == 0) ++z;
+        for (int k = 0; k <= z; ++k) ++cnt[k];
+    }
+    if (N == 1) { e_T[0] = 1; return 1; }  // set.py:171-172
+    for (int k = 0; k <= m; ++k) e_T[k] = cnt[k];
+    return m + 1;
+}
+
+int lpfnt_ordinal_embedding(const int64_t *As, int64_t Ns, const int64_t *Ab, int64_t Nb, int m, int64_t *phi) {
+    if (!As || !Ab || !phi || m < 1) { set_error("ordinal_embedding: bad arguments"); return LPFNT_EINVAL; }
+    auto cmp = [m](const int64_t *a, const int64_t *b) {
+        for (int j = m - 1; j >= 0; --j) {
+            if (a[j] < b[j]) return -1;
+            if (a[j] > b[j]) return 1;
+        }
+        return 0;
+    };
+    int64_t j = 0;
+    for (int64_t i = 0; i < Ns; ++i) {
+        while (j < Nb && cmp(Ab + j * m, As + i * m) < 0) ++j;
+        if (j >= Nb || cmp(Ab + j * m, As + i * m) != 0) {
+            set_error("ordinal_embedding: the small set is not contained in the large one");
+            return LPFNT_EINVAL;
+        }
+        phi[i] = j;
+    }
+    return LPFNT_OK;
+}
+
+int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index) {
+    if (!index) { set_error("index pointer is null"); return LPFNT_EINVAL; }
+    *index = nullptr;
+    if (!A) { set_error("index_create: A is null"); return LPFNT_EINVAL; }
+    lpfnt_index *ix = new lpfnt_index();
+    if (!ix->hx.build(A, N, m, n)) { delete ix; return LPFNT_EINVAL; }
+    *index = ix;
+    return LPFNT_OK;
+}
+int lpfnt_index_destroy(lpfnt_index *index) { delete index; return LPFNT_OK; }
+int64_t lpfnt_index_size(const lpfnt_index *index, int what, int h) {
+    const void *p; size_t b; int64_t c;
+    if (!index || !table_view(index, what, h, &p, &b, &c)) { set_error("index_size: no such table"); return LPFNT_EINVAL; }
+    return c;
+}
+int lpfnt_index_copy(const lpfnt_index *index, int what, int h, void *dst) {
+    const void *p; size_t b; int64_t c;
+    if (!index || !dst || !table_view(index, what, h, &p, &b, &c)) { set_error("index_copy: no such table"); return LPFNT_EINVAL; }
+    std::memcpy(dst, p, b);
+    return LPFNT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// Internal declarations shared by the translation units of liblpfnt.so.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/lpfnt.h"
+
+namespace lpfnt {
+
+constexpr int kMaxDim = 12;     // spatial dimensions supported by the fast kernels' line descriptors
+constexpr int kMaxRegT = 32;    // longest fibre held in registers by the unrolled kernels (n+1 <= 32)
+
+void set_error(const std::string &msg);
+
+struct FibEnt {  // one line of a fibre: element offset of the line start and its length
+    int32_t off;
+    int32_t len;
+};
+
+// Per-coordinate (h >= 1) grouping of the lines into fibres (lines that differ only in a_h,
+// ordered by a_h).  One GPU thread owns one element-fibre = (fibre, lane a_0).
+struct DimTable {
+    int32_t num_fibres = 0;
+    int64_t num_threads = 0;             // sum over fibres of the length of their first line
+    int32_t max_lines = 0;               // longest fibre (in lines)
+    std::vector<int32_t> fib_ptr;        // num_fibres + 1, CSR into ent
+    std::vector<FibEnt> ent;             // N_1 entries
+    std::vector<int32_t> thr_start;      // num_fibres + 1, prefix sum of lanes per fibre
+    std::vector<int32_t> thr_fib;        // num_threads, thread -> fibre
+};
+
+// Host-side index structure derived from the multi-index array A (colex order).
+struct HostIndex {
+    int m = 0, n = 0;
+    int64_t N = 0, N1 = 0;
+    int32_t max_line = 0;
+    std::vector<int32_t> line_off;       // N_1 + 1 (cs_T)
+    std::vector<int64_t> level_size;     // m + 1: N_0, N_1, ..., N_{m-1}, 1
+    std::vector<DimTable> dims;          // index h = 0..m-1 (entry 0 unused)
+    std::vector<uint8_t> line_alpha;     // N_1 * (m-1): (a_1..a_{m-1}) of every line, for eval (n <= 255)
+    // returns false (and sets the error) if A is not a colex-ordered downward-closed set
+    bool build(const int64_t *A, int64_t N, int m, int n);
+};
+
+}  // namespace lpfnt

@@ -1,0 +1,63 @@
+// Instantiates the register-fibre sweep kernels for one fibre capacity LPFNT_MAXT.
+#include <cstring>
+
+#include "sweep_launch.h"
+
+#ifndef LPFNT_MAXT
+#error "compile with -DLPFNT_MAXT=<8|16|24|32>"
+#endif
+
+namespace lpfnt {
+
+namespace {
+constexpr int T = LPFNT_MAXT;
+
+template <int MODE, bool FMA>
+cudaError_t line_launch(const LineSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
+    dim3 grid((a.num_lines + kSweepThreads - 1) / kSweepThreads, batch);
+    k_sweep_lines<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
+    return cudaGetLastError();
+}
+template <int MODE, bool FMA>
+cudaError_t fibre_launch(const FibreSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
+    dim3 grid((a.num_threads + kSweepThreads - 1) / kSweepThreads, batch);
+    k_sweep_fibres<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <>
+cudaError_t launch_line_sweep<T>(int mode, bool fma, const LineSweepArgs &a, const double *tri, int batch, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? line_launch<kLowerMatvec, true>(a, M, batch, s) : line_launch<kLowerMatvec, false>(a, M, batch, s);
+        case kUpperMatvec: return fma ? line_launch<kUpperMatvec, true>(a, M, batch, s) : line_launch<kUpperMatvec, false>(a, M, batch, s);
+        case kLowerSolve: return line_launch<kLowerSolve, false>(a, M, batch, s);
+        case kUpperSolve: return line_launch<kUpperSolve, false>(a, M, batch, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <>
+cudaError_t launch_fibre_sweep<T>(int mode, bool fma, const FibreSweepArgs &a, const double *tri, int batch, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? fibre_launch<kLowerMatvec, true>(a, M, batch, s) : fibre_launch<kLowerMatvec, false>(a, M, batch, s);
+        case kUpperMatvec: return fma ? fibre_launch<kUpperMatvec, true>(a, M, batch, s) : fibre_launch<kUpperMatvec, false>(a, M, batch, s);
+        case kLowerSolve: return fibre_launch<kLowerSolve, false>(a, M, batch, s);
+        case kUpperSolve: return fibre_launch<kUpperSolve, false>(a, M, batch, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+#if LPFNT_MAXT == 8
+cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s) {
+    dim3 grid((a.num_threads + 127) / 128, batch);
+    k_sweep_generic<<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace lpfnt

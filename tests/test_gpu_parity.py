@@ -1,0 +1,298 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against (a) the reference's recorded
+outputs in tests/golden/ and (b) the CPU oracle on the same seeded inputs.
+
+Bars
+----
+* index tables, permutation, nodes, packed matrices: bit-exact (np.array_equal)
+* fnt (default and precomputation=False), dx, dxT, ifnt(exact_ifnt=True): bit-exact
+* ifnt (default, FMA) : max|new-ref| / max|ref| <= 1e-13   (north star: 1e-12)
+* eval (nested Horner): max|new-ref| / max|ref| <= 1e-12
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, case_kwargs, golden_cases, load_case
+
+pytestmark = pytest.mark.gpu
+
+TOL_IFNT_FMA = 1e-13
+TOL_EVAL = 1e-12
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def T():
+    import lpfun_b200
+
+    return lpfun_b200.Transform
+
+
+def make(T, g, **kw):
+    kwargs = case_kwargs(g)
+    kwargs.update(report=False, precompilation=False)
+    kwargs.update(kw)
+    return T(**kwargs)
+
+
+@pytest.mark.parametrize("name", golden_cases("newton"))
+def test_golden_case(T, name):
+    g = load_case(name)
+    t = make(T, g, exact_ifnt=True)
+    m = int(g["m"])
+    # --- plan tables ---
+    assert np.array_equal(t.multi_index_set, g["A"].astype(np.int64))
+    assert np.array_equal(t.tube, g["T"])
+    assert np.array_equal(t.nodes, g["x"]) and np.array_equal(t.leja_order, g["leja_order"])
+    if bool(g["colex"]):
+        assert np.array_equal(t.colex_order, g["P"])
+    else:
+        assert t.colex_order is None
+    assert len(t) == int(g["N"])
+    # --- fnt: bit exact, batched call == row by row ---
+    got = t.fnt(g["values"])
+    assert got.shape == g["fnt"].shape
+    nbits = int(np.sum(got != g["fnt"]))
+    assert nbits == 0, f"{nbits} coefficients differ, rel {relmax(got, g['fnt']):.2e}"
+    assert np.array_equal(t.fnt(g["values"][0]), g["fnt"][0])
+    assert np.array_equal(t.fnt(g["rnd"]), g["fnt_rnd"])
+    # --- ifnt exact + FMA ---
+    assert np.array_equal(t.ifnt(g["fnt"]), g["ifnt"])
+    assert np.array_equal(t.ifnt(g["rnd"]), g["ifnt_rnd"])
+    tf = make(T, g)  # default: FMA ifnt
+    assert relmax(tf.ifnt(g["fnt"]), g["ifnt"]) <= TOL_IFNT_FMA
+    # --- dx / dxT ---
+    inf_multi = np.isinf(float(g["p"])) and m > 1  # reference folds descending there (molecules.py:290-294)
+    for key in g.files:
+        if key.startswith("dx_"):
+            _, i, k = key.split("_")
+            out = t.dx(g["fnt"][0], int(i), int(k))
+            if inf_multi:
+                assert relmax(out, g[key]) <= 1e-13, key
+            else:
+                assert np.array_equal(out, g[key]), key
+        elif key.startswith("dxT_"):
+            _, i, k = key.split("_")
+            assert np.array_equal(t.dxT(g["rnd"], int(i), int(k)), g[key]), key
+    # --- eval ---
+    assert relmax(t.eval(g["fnt"][0], g["points"]), g["eval"]) <= TOL_EVAL
+    assert relmax(t.eval(g["dx_0_1"], g["points"]), g["eval_dx0"]) <= TOL_EVAL
+    assert t.launch_count > 0
+    t.close()
+    tf.close()
+
+
+@pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d2n7_inf", "d1n12", "d3n12_solve"])
+def test_generic_kernels_match_too(T, name):
+    """force_generic routes every op through the unbounded-n fallback kernels."""
+    g = load_case(name)
+    t = make(T, g, exact_ifnt=True)
+    t.set_option("force_generic", 1)
+    assert np.array_equal(t.fnt(g["values"]), g["fnt"])
+    assert np.array_equal(t.ifnt(g["fnt"]), g["ifnt"])
+    m = int(g["m"])
+    if not (np.isinf(float(g["p"])) and m > 1):
+        assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
+    assert np.array_equal(t.dxT(g["rnd"], 0, 1), g["dxT_0_1"])
+    assert relmax(t.eval(g["fnt"][0], g["points"]), g["eval"]) <= TOL_EVAL
+    t.close()
+
+
+def test_device_tensor_path_and_inplace(T):
+    import torch
+
+    g = load_case("c2_d3n20_leja")
+    t = make(T, g, exact_ifnt=True)
+    v = torch.as_tensor(g["values"], device="cuda")
+    c = t.fnt(v)
+    assert c.is_cuda and np.array_equal(c.cpu().numpy(), g["fnt"])
+    r = t.ifnt(c)
+    assert np.array_equal(r.cpu().numpy(), g["ifnt"])
+    d = t.dx(c[0], 2, 1)
+    assert np.array_equal(d.cpu().numpy(), g["dx_2_1"])
+    e = t.eval(c[0], torch.as_tensor(g["points"], device="cuda"))
+    assert relmax(e.cpu().numpy(), g["eval"]) <= TOL_EVAL
+    # in-place through the raw C ABI (in == out), with the colex permutation active
+    from lpfun_b200 import _native as nat
+
+    buf = v.clone()
+    stream = torch.cuda.current_stream().cuda_stream
+    nat.check(nat.lib().lpfnt_fnt(t._plan, buf.data_ptr(), buf.data_ptr(), buf.shape[0], 1, stream))
+    assert np.array_equal(buf.cpu().numpy(), g["fnt"])
+    nat.check(nat.lib().lpfnt_ifnt(t._plan, buf.data_ptr(), buf.data_ptr(), buf.shape[0], 0, 1, stream))
+    assert np.array_equal(buf.cpu().numpy(), g["ifnt"])
+    t.close()
+
+
+def test_operator_level_entry_points(T):
+    """lpfnt_itransform / lpfnt_transform / lpfnt_dtransform with caller-supplied packed matrices."""
+    from lpfun_b200 import _native as nat
+
+    g = load_case("d4n8")
+    t = make(T, g)
+    L = nat.lib()
+    x = np.ascontiguousarray(g["values"][0])
+    out = np.empty_like(x)
+    inv = np.ascontiguousarray(g["inv_Vx_lt"])
+    nat.check(L.lpfnt_itransform(t._plan, inv.ctypes.data, nat.LPFNT_LOWER, nat.ARITH_EXACT, x.ctypes.data, out.ctypes.data, 1, 0, 0, 0, None))
+    assert np.array_equal(out, g["fnt"][0])  # this case has colex_order=False
+    gs = load_case("d4n8_solve")
+    V = np.ascontiguousarray(gs["Vx_lt"])
+    nat.check(L.lpfnt_transform(t._plan, V.ctypes.data, nat.LPFNT_LOWER, x.ctypes.data, out.ctypes.data, 1, 0, 0, 0, None))
+    assert np.array_equal(out, gs["fnt"][0])
+    D = np.ascontiguousarray(g["Dx_lt1"])
+    c = np.ascontiguousarray(g["fnt"][0])
+    nat.check(L.lpfnt_dtransform(t._plan, D.ctypes.data, nat.LPFNT_UPPER, nat.ARITH_EXACT, 3, c.ctypes.data, out.ctypes.data, 1, 0, None))
+    assert np.array_equal(out, g["dx_3_2"])
+    with pytest.raises(ValueError):
+        nat.check(L.lpfnt_dtransform(t._plan, D.ctypes.data, nat.LPFNT_UPPER, 0, 4, c.ctypes.data, out.ctypes.data, 1, 0, None))
+    t.close()
+
+
+def test_error_behaviour(T):
+    with pytest.raises(ValueError):
+        T(0, 4, report=False)
+    with pytest.raises(ValueError):
+        T(2, 4, 3.0, report=False)
+    with pytest.raises(ValueError):
+        T(2, 4, basis="legendre", report=False)
+    with pytest.raises(ValueError):
+        T(3, 30, threshold=100, report=False)
+    with pytest.raises(ValueError):
+        T(2, 4, nodes=lambda k: np.zeros(k), report=False)
+    t = T(2, 4, report=False)
+    z = np.zeros(len(t))
+    with pytest.raises(ValueError):
+        t.dx(z, 2)
+    with pytest.raises(ValueError):
+        t.dx(z, 0, 4)
+    with pytest.raises(ValueError):
+        t.fnt(np.zeros(len(t) + 5))  # the reference corrupts the heap here
+    with pytest.raises(ValueError):
+        t.eval(z, np.zeros((3, 5)))
+    assert t.eval(z, np.zeros((0, 2))).shape == (0,)
+    t.close()
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own property tests (test.py:45-151), Newton basis, both precomputation modes
+# ---------------------------------------------------------------------------------------
+GRID = [(m, p, pr) for m in (1, 2, 3, 4, 5, 6) for p in (1.0, 2.0, np.inf) for pr in (True, False)]
+
+
+@pytest.mark.parametrize("m, p, pr", GRID)
+def test_reference_property_suite(T, m, p, pr):
+    rng = np.random.default_rng(100 * m + int(pr))
+    for n in (4, 6, 8) if m < 6 else (4, 5):
+        if np.isinf(p) and (n + 1) ** m > 300000:
+            continue
+        t = T(m, n, p, precomputation=pr, precompilation=False, colex_order=False, report=False)
+        N = len(t)
+        # test_fnt_ifnt
+        f = rng.random(N)
+        assert np.linalg.norm(t.ifnt(t.fnt(f)) - f) < 1e-8
+        # test_dx
+        vals = np.sum(t.grid ** (n - 1), axis=1)
+        c = t.fnt(vals)
+        for k in (1, 2, 3):
+            fac = np.prod([n - 1 - q for q in range(k)])
+            for i in range(m):
+                want = fac * t.grid[:, i] ** (n - 1 - k)
+                assert np.linalg.norm(t.ifnt(t.dx(c, i, k)) - want) < 1e-6
+        # test_dxT (adjoint identity)
+        for k in (1, 2, 3):
+            for i in range(m):
+                x, y = rng.standard_normal(N), rng.standard_normal(N)
+                assert abs(np.dot(t.dx(x, i, k), y) - np.dot(x, t.dxT(y, i, k))) < 1e-6
+        t.close()
+        # test_eval (degree n+1, cubic)
+        t = T(m, n + 1, p, precomputation=pr, precompilation=False, colex_order=False, report=False)
+        c = t.fnt(np.sum(t.grid ** 3, axis=1))
+        pts = rng.random((10, m))
+        assert np.max(np.abs(t.eval(c, pts) - np.sum(pts ** 3, axis=1))) < 1e-6
+        t.close()
+
+
+def test_tutorial_short_config1(T):
+    """BASELINE config 1: Transform(2, 10), sin(x)cos(y): fnt -> dx -> eval / ifnt."""
+    t = T(spatial_dimension=2, polynomial_degree=10, report=False)
+    g = load_case("c1_d2n10")
+    v = np.sin(t.grid[:, 0]) * np.cos(t.grid[:, 1])
+    assert np.array_equal(v, g["values"][0])
+    c = t.fnt(v)
+    d = t.dx(c, i=0, k=1)
+    assert np.array_equal(c, g["fnt"][0]) and np.array_equal(d, g["dx_0_1"])
+    rec = t.ifnt(d)
+    assert np.max(np.abs(rec - np.cos(t.grid[:, 0]) * np.cos(t.grid[:, 1]))) < 1e-6
+    pts = g["points"]
+    assert np.max(np.abs(t.eval(d, pts) - np.cos(pts[:, 0]) * np.cos(pts[:, 1]))) < 1e-6
+    t.close()
+
+
+def test_c3_d6n20_sampled(T):
+    """BASELINE config 3 at FULL size (N = 6 974 412): sampled outputs of the reference, plus a
+    size-independent property (round trip)."""
+    import hashlib
+
+    g = np.load(os.path.join(GOLDEN, "c3_d6n20.npz"))
+    t = T(6, 20, report=False, precompilation=False, exact_ifnt=True)
+    assert len(t) == int(g["N"])
+    gr = t.grid
+    w = np.arange(1, 7, dtype=np.float64) / 6.0
+    vals = np.exp(-np.sum(gr * gr, axis=1)) * np.sin(gr @ w)
+    idx = g["idx"]
+    assert np.array_equal(vals[idx], g["values_s"])
+    c = t.fnt(vals)
+    assert np.array_equal(c[idx], g["fnt_s"])
+    assert hashlib.sha256(c.tobytes()).hexdigest() == str(g["fnt_sha"])
+    r = t.ifnt(c)
+    assert hashlib.sha256(r.tobytes()).hexdigest() == str(g["ifnt_sha"])
+    assert np.max(np.abs(r - vals)) == float(g["roundtrip_err"])
+    t.close()
+
+
+def test_c4_batched_vs_oracle(T):
+    """BASELINE config 4 shape (d=3, n=30), a batch of 64 seeded functions: CUDA vs the CPU oracle."""
+    from oracle import oracle as O
+
+    t = T(3, 30, report=False, precompilation=False, exact_ifnt=True)
+    o = O.OracleTransform(3, 30, 2.0)
+    assert np.array_equal(o.P, t.colex_order) and np.array_equal(o.grid, t.grid)
+    rng = np.random.default_rng(1234)
+    B = 64
+    a = rng.uniform(0.5, 1.0, size=(B, 4))
+    w = rng.uniform(-3, 3, size=(B, 4, 3))
+    ph = rng.uniform(0, 2 * np.pi, size=(B, 4))
+    vals = np.stack([np.sum(a[b][None, :] * np.sin(t.grid @ w[b].T + ph[b][None, :]), axis=1) for b in range(B)])
+    c = t.fnt(vals)
+    r = t.ifnt(c)
+    for b in range(0, B, 7):
+        cb = o.fnt(vals[b])
+        assert np.array_equal(c[b], cb)
+        assert np.array_equal(r[b], o.ifnt(cb))
+    # linearity of the batched path (size-independent property)
+    s = t.ifnt(c[0] + 2.0 * c[1])
+    assert relmax(s, r[0] + 2.0 * r[1]) < 1e-12
+    t.close()
+
+
+def test_c5_dx_eval_vs_oracle(T):
+    """BASELINE config 5 shape (d=4, n=20): dx along every coordinate and eval at 4096 random points."""
+    from oracle import oracle as O
+
+    g = load_case("c5_d4n20")
+    t = make(T, g)
+    c = g["fnt"][0]
+    o = O.Sweeper(g["A"].astype(np.int64))
+    rng = np.random.default_rng(1234)
+    pts = rng.random((4096, 4)) * 2 - 1
+    for i in range(4):
+        d = t.dx(c, i, 1)
+        assert np.array_equal(d, g[f"dx_{i}_1"])
+    want = o.eval(g["dx_0_1"], g["x"], pts, 20)
+    assert relmax(t.eval(g["dx_0_1"], pts), want) <= TOL_EVAL
+    t.close()
