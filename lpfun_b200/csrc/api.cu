@@ -336,7 +336,8 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
     }
     if (!hx.line_alpha.empty())
         if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
-    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255) p->hA.assign(A, A + N * m);  // generic eval needs A
+    // the generic eval needs A on the device; keep a host copy when that path can be reached
+    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255 || N * m <= (int64_t(1) << 23)) p->hA.assign(A, A + N * m);
     if (nodes && (rc = upload(&p->d_nodes, nodes, size_t(n + 1), p))) return fail(rc);
     {
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_mat), sizeof(double) * ts);
