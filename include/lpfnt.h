@@ -92,7 +92,11 @@ enum {
     LPFNT_TAB_THR_START = 3,  /* F_h + 1 : first thread (element-fibre) of each fibre          */
     LPFNT_TAB_THR_FIB = 4,    /* #threads: thread -> fibre                                     */
     LPFNT_TAB_LINE_ALPHA = 5, /* N_1 * (m-1) uint8 : (a_1..a_{m-1}) of every line (eval)       */
-    LPFNT_TAB_LEVEL_SIZE = 6  /* m + 1 int64 : N_0, N_1, ..., 1                                */
+    LPFNT_TAB_LEVEL_SIZE = 6, /* m + 1 int64 : N_0, N_1, ..., 1                                */
+    LPFNT_TAB_TILE_FIB = 7,   /* tiles + 1: tile -> first fibre (a tile = consecutive fibres of h) */
+    LPFNT_TAB_TILE_ITEMS = 8, /* #threads uint32: per tile its element-fibres, longest first:
+                                 row (relative to the tile) | lane << 16 | length << 24         */
+    LPFNT_TAB_TILE_ROWS0 = 9  /* N_1 uint32: per tile its rows, longest first: row | len << 24   */
 };
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);
@@ -124,10 +128,12 @@ int64_t lpfnt_plan_device_bytes(const lpfnt_plan *plan);
 /* number of kernel launches enqueued by this plan since creation */
 int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
 /* options: "force_generic" (1 = route every op through the unbounded-n fallback kernels),
- *          "trace" (1 = record a CUDA-event pair around every kernel launch) */
+ *          "trace" (1 = record a CUDA-event pair around every kernel launch),
+ *          "use_tiles" (0 = per-coordinate line/fibre kernels instead of the row-tile kernels),
+ *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line
- * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4 fused tile sweep) and its device time in ms.
+ * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4 row-tile sweep, 5 row-tile sweep fused with coordinate 0) and its device time in ms.
  * Synchronises on the recorded events.  *count receives the number of records seen. */
 int lpfnt_plan_trace_read(lpfnt_plan *plan, int max_records, int *labels, float *ms, int *count);
 

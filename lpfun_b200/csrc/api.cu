@@ -29,7 +29,9 @@ namespace {
 struct DeviceDim {
     int32_t *thr_fib = nullptr, *thr_start = nullptr, *fib_ptr = nullptr;
     int2 *ent = nullptr;
-    int32_t num_threads = 0, max_lines = 0;
+    int32_t *tile_fib = nullptr;
+    uint32_t *items = nullptr, *rows0 = nullptr;
+    int32_t num_threads = 0, max_lines = 0, num_tiles = 0;
 };
 
 int tri_size(int n1) { return n1 * (n1 + 1) / 2; }
@@ -58,6 +60,8 @@ struct lpfnt_plan {
     int64_t launches = 0;
     int64_t table_bytes = 0;
     int force_generic = 0;
+    int use_tiles = 1;                       // row-tile kernels (sorted work items, fused coordinate 0)
+    int64_t l2_chunk_bytes = int64_t(32) << 20;  // batched multi-pass transforms run in chunks this large
     // optional per-launch tracing (CUDA events around every kernel launch)
     int trace = 0;
     struct TraceRec { int label; cudaEvent_t a, b; };
@@ -138,11 +142,13 @@ int sweep_mode(const SweepSpec &s) {
 }
 
 // One sweep along coordinate h: src -> dst (device pointers, may alias when no perm is used).
-int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, const double *src, double *dst, int64_t batch,
+int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const double *src, double *dst, int64_t batch,
                bool gather, bool scatter, cudaStream_t s) {
     const int n1 = p->n + 1;
     const int mode = sweep_mode(spec);
-    const int len = (h == 0) ? p->max_line : p->dd[h].max_lines;
+    const int len = (h == 0) ? p->max_line : std::max(p->dd[h].max_lines, fuse0 ? p->max_line : 0);
+    const bool tiles = h >= 1 && p->use_tiles && p->dd[h].num_tiles > 0;
+    if (fuse0 && !tiles) { set_error("internal: fused coordinate-0 sweep needs the tile kernel"); return LPFNT_EINVAL; }
     const int cap = p->force_generic ? 0 : pick_cap(std::max(len, 1));
     std::vector<double> tri;
     if (cap) repack(spec.packed, n1, spec.kind, cap, tri);
@@ -155,7 +161,7 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, const double *src, d
         const double *in = src + b0 * p->N;
         double *out = dst + b0 * p->N;
         cudaError_t e = cudaSuccess;
-        trace_begin(p, (cap == 0 ? 200 : (h == 0 ? 0 : 100)) + h, s);
+        trace_begin(p, (cap == 0 ? 200 : (h == 0 ? 0 : (tiles ? (fuse0 ? 500 : 400) : 100))) + h, s);
         if (cap == 0) {
             GenericArgs a{};
             a.in = in; a.out = out; a.mat = p->d_mat; a.line_off = p->d_line_off;
@@ -177,6 +183,16 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, const double *src, d
                 case 24: e = launch_line_sweep<24>(mode, spec.fma, a, tri.data(), nb, s); break;
                 default: e = launch_line_sweep<32>(mode, spec.fma, a, tri.data(), nb, s); break;
             }
+        } else if (tiles) {
+            const DeviceDim &d = p->dd[h];
+            TileSweepArgs a{in, out, d.tile_fib, d.fib_ptr, d.thr_start, d.ent, d.items, d.rows0,
+                            gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N};
+            switch (cap) {
+                case 8: e = launch_tile_sweep<8>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
+                case 16: e = launch_tile_sweep<16>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
+                case 24: e = launch_tile_sweep<24>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
+                default: e = launch_tile_sweep<32>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
+            }
         } else {
             if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
             const DeviceDim &d = p->dd[h];
@@ -197,37 +213,54 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, const double *src, d
 
 // Device-resident pipeline: sweeps along `dims` (ascending), optional colex gather on the way
 // in and scatter on the way out.  in/out may alias.
+//
+// Pass plan: with the tile kernels the coordinate-0 sweep rides along with the coordinate-1 pass
+// (one pass fewer); every remaining coordinate is one pass.  Passes 2.. run in place.  A batched
+// multi-pass transform is cut into chunks of functions of ~l2_chunk_bytes so that the passes
+// after the first find their input in the 126 MB L2 instead of HBM.
+struct Pass { int h; bool fuse0; };
+
 int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
                int64_t batch, bool gather, bool scatter, cudaStream_t s) {
     gather = gather && p->has_perm;
     scatter = scatter && p->has_perm;
-    const size_t bytes = size_t(batch) * size_t(p->N) * sizeof(double);
-    const int nd = int(dims.size());
-    if (nd == 0) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
+    if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
-    if (!gather && !scatter) {
-        for (int q = 0; q < nd; ++q) {
-            int rc = launch_dim(p, spec, dims[q], q == 0 ? in : out, out, batch, false, false, s);
+    std::vector<Pass> passes;
+    {
+        size_t q = 0;
+        const bool can_tile = !p->force_generic && p->use_tiles && p->m >= 2 && p->dd[1].num_tiles > 0 &&
+                              pick_cap(std::max(p->max_line, p->dd[1].max_lines)) > 0;
+        if (dims.size() >= 2 && dims[0] == 0 && dims[1] == 1 && can_tile) { passes.push_back({1, true}); q = 2; }
+        for (; q < dims.size(); ++q) passes.push_back({dims[q], false});
+    }
+    const int np = int(passes.size());
+    const size_t fbytes = size_t(p->N) * sizeof(double);
+    int64_t chunk = batch;
+    if (np >= 2 && p->l2_chunk_bytes > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, p->l2_chunk_bytes / int64_t(fbytes)));
+    const bool permuting = gather || scatter;
+    // a permuting pass must not run in place; with >= 2 passes the middle buffer absorbs that
+    const bool need_mid = (np == 1) ? (permuting && in == out) : (scatter || (permuting && in == out));
+    double *mid_base = nullptr;
+    if (need_mid) { int rc = ensure_ws(p, 2, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[2]; }
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+        const int64_t nb = std::min(chunk, batch - b0);
+        const double *cin = in + b0 * p->N;
+        double *cout = out + b0 * p->N;
+        if (np == 1) {
+            double *dst = need_mid ? mid_base : cout;
+            int rc = launch_dim(p, spec, passes[0].h, passes[0].fuse0, cin, dst, nb, gather, scatter, s);
+            if (rc) return rc;
+            if (dst != cout) CK(cudaMemcpyAsync(cout, dst, size_t(nb) * fbytes, cudaMemcpyDeviceToDevice, s));
+            continue;
+        }
+        double *mid = need_mid ? mid_base : cout;
+        for (int q = 0; q < np; ++q) {
+            const bool first = (q == 0), last = (q == np - 1);
+            int rc = launch_dim(p, spec, passes[q].h, passes[q].fuse0, first ? cin : mid, last ? cout : mid, nb,
+                                first && gather, last && scatter, s);
             if (rc) return rc;
         }
-        return LPFNT_OK;
-    }
-    // with a permutation the permuting sweep must not run in place
-    if (nd == 1) {
-        double *dst = out;
-        if (in == out) { int rc = ensure_ws(p, 2, bytes); if (rc) return rc; dst = p->ws[2]; }
-        int rc = launch_dim(p, spec, dims[0], in, dst, batch, gather, scatter, s);
-        if (rc) return rc;
-        if (dst != out) CK(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToDevice, s));
-        return LPFNT_OK;
-    }
-    // first sweep: in -> mid ; middle sweeps in place on mid ; last sweep: mid -> out
-    double *mid = out;
-    if (scatter || in == out) { int rc = ensure_ws(p, 2, bytes); if (rc) return rc; mid = p->ws[2]; }
-    for (int q = 0; q < nd; ++q) {
-        const bool first = (q == 0), last = (q == nd - 1);
-        int rc = launch_dim(p, spec, dims[q], first ? in : mid, last ? out : mid, batch, first && gather, last && scatter, s);
-        if (rc) return rc;
     }
     return LPFNT_OK;
 }
@@ -333,6 +366,12 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if ((rc = upload(&d.fib_ptr, D.fib_ptr.data(), D.fib_ptr.size(), p))) return fail(rc);
         static_assert(sizeof(FibEnt) == sizeof(int2), "FibEnt must match int2");
         if ((rc = upload(&d.ent, reinterpret_cast<const int2 *>(D.ent.data()), D.ent.size(), p))) return fail(rc);
+        if (!D.tile_fib.empty()) {
+            d.num_tiles = int32_t(D.tile_fib.size()) - 1;
+            if ((rc = upload(&d.tile_fib, D.tile_fib.data(), D.tile_fib.size(), p))) return fail(rc);
+            if ((rc = upload(&d.items, D.items.data(), D.items.size(), p))) return fail(rc);
+            if ((rc = upload(&d.rows0, D.rows0.data(), D.rows0.size(), p))) return fail(rc);
+        }
     }
     if (!hx.line_alpha.empty())
         if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
@@ -359,6 +398,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
+        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0);
     }
     for (int s = 0; s < 3; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -376,6 +416,8 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_tiles") == 0) { p->use_tiles = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "l2_chunk_bytes") == 0) { p->l2_chunk_bytes = value; return LPFNT_OK; }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;
 }

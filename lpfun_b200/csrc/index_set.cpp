@@ -251,6 +251,58 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
             for (int32_t t = D.thr_start[g]; t < D.thr_start[g + 1]; ++t) D.thr_fib[t] = g;
     }
 
+
+    // ---- row tiles: consecutive fibres grouped so that a CTA stages <= kTileRows lines in shared
+    //      memory and owns <= kTileItems element-fibres; inside a tile the element-fibres (and, for
+    //      the fused coordinate-0 sweep, the rows) are ordered by length, longest first, so that the
+    //      32 lanes of a warp run triangles of (nearly) the same size. ----
+    for (int h = 1; h < m; ++h) {
+        DimTable &D = dims[h];
+        if (D.max_lines > 255 || max_line > 255) continue;  // descriptors pack lengths into 8 bits
+        D.tile_fib.clear();
+        D.tile_fib.push_back(0);
+        int32_t rows = 0, items = 0;
+        for (int32_t f = 0; f < D.num_fibres; ++f) {
+            const int32_t fr = D.fib_ptr[f + 1] - D.fib_ptr[f];
+            const int32_t fi = D.thr_start[f + 1] - D.thr_start[f];
+            if (f > D.tile_fib.back() && (rows + fr > kTileRows || items + fi > kTileItems)) {
+                D.tile_fib.push_back(f);
+                rows = 0;
+                items = 0;
+            }
+            rows += fr;
+            items += fi;
+        }
+        D.tile_fib.push_back(D.num_fibres);
+        const int32_t ntiles = static_cast<int32_t>(D.tile_fib.size()) - 1;
+        D.items.resize(D.num_threads);
+        D.rows0.resize(N1);
+        std::vector<uint32_t> tmp;
+        for (int32_t tl = 0; tl < ntiles; ++tl) {
+            const int32_t f0 = D.tile_fib[tl], f1 = D.tile_fib[tl + 1];
+            const int32_t r0 = D.fib_ptr[f0], r1 = D.fib_ptr[f1];
+            const int32_t i0 = D.thr_start[f0];
+            // element-fibres of the tile
+            tmp.clear();
+            for (int32_t f = f0; f < f1; ++f) {
+                const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
+                const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
+                for (int32_t lane = 0; lane < lanes; ++lane) {
+                    int32_t t = 0;
+                    while (t < nl && D.ent[p0 + t].len > lane) ++t;
+                    tmp.push_back(uint32_t(p0 - r0) | (uint32_t(lane) << 16) | (uint32_t(t) << 24));
+                }
+            }
+            std::stable_sort(tmp.begin(), tmp.end(), [](uint32_t a, uint32_t b) { return (a >> 24) > (b >> 24); });
+            std::copy(tmp.begin(), tmp.end(), D.items.begin() + i0);
+            // rows of the tile (coordinate-0 sweep)
+            tmp.clear();
+            for (int32_t r = r0; r < r1; ++r) tmp.push_back(uint32_t(r - r0) | (uint32_t(D.ent[r].len) << 24));
+            std::stable_sort(tmp.begin(), tmp.end(), [](uint32_t a, uint32_t b) { return (a >> 24) > (b >> 24); });
+            std::copy(tmp.begin(), tmp.end(), D.rows0.begin() + r0);
+        }
+    }
+
     // ---- line descriptors for eval ----
     line_alpha.clear();
     if (n <= 255 && m >= 2) {
@@ -287,6 +339,9 @@ bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t
     if (what == LPFNT_TAB_FIB_ENT) return set(D.ent.data(), 8, D.ent.size(), int64_t(2 * D.ent.size()));
     if (what == LPFNT_TAB_THR_START) return set(D.thr_start.data(), 4, D.thr_start.size(), int64_t(D.thr_start.size()));
     if (what == LPFNT_TAB_THR_FIB) return set(D.thr_fib.data(), 4, D.thr_fib.size(), int64_t(D.thr_fib.size()));
+    if (what == LPFNT_TAB_TILE_FIB) return set(D.tile_fib.data(), 4, D.tile_fib.size(), int64_t(D.tile_fib.size()));
+    if (what == LPFNT_TAB_TILE_ITEMS) return set(D.items.data(), 4, D.items.size(), int64_t(D.items.size()));
+    if (what == LPFNT_TAB_TILE_ROWS0) return set(D.rows0.data(), 4, D.rows0.size(), int64_t(D.rows0.size()));
     return false;
 }
 }  // namespace

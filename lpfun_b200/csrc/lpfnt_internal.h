@@ -10,6 +10,8 @@ namespace lpfnt {
 
 constexpr int kMaxDim = 12;     // spatial dimensions supported by the fast kernels' line descriptors
 constexpr int kMaxRegT = 32;    // longest fibre held in registers by the unrolled kernels (n+1 <= 32)
+constexpr int kTileRows = 128;  // lines staged in shared memory by one CTA of the tile kernel
+constexpr int kTileItems = 128; // element-fibres per CTA (= threads per CTA)
 
 void set_error(const std::string &msg);
 
@@ -28,6 +30,11 @@ struct DimTable {
     std::vector<FibEnt> ent;             // N_1 entries
     std::vector<int32_t> thr_start;      // num_fibres + 1, prefix sum of lanes per fibre
     std::vector<int32_t> thr_fib;        // num_threads, thread -> fibre
+    // row tiles (see HostIndex::build): tile -> fibre range; per tile the element-fibres and rows
+    // sorted by length.  item = row_rel | lane << 16 | t << 24 ; row0 = row_rel | len << 24
+    std::vector<int32_t> tile_fib;       // num_tiles + 1
+    std::vector<uint32_t> items;         // num_threads (indexed like the threads: thr_start[f0] + j)
+    std::vector<uint32_t> rows0;         // N_1 (indexed like ent: fib_ptr[f0] + j)
 };
 
 // Host-side index structure derived from the multi-index array A (colex order).

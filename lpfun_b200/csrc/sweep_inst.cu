@@ -24,7 +24,27 @@ cudaError_t fibre_launch(const FibreSweepArgs &a, const PackedTri<T> &M, int bat
     k_sweep_fibres<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
 }
+template <int MODE, bool FMA>
+cudaError_t tile_launch(bool dim0, const TileSweepArgs &a, const PackedTri<T> &M, int num_tiles, int batch, cudaStream_t s) {
+    dim3 grid(num_tiles, batch);
+    if (dim0) k_sweep_tiles<T, MODE, FMA, true, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
+    else k_sweep_tiles<T, MODE, FMA, false, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
+    return cudaGetLastError();
+}
 }  // namespace
+
+template <>
+cudaError_t launch_tile_sweep<T>(int mode, bool fma, bool dim0, const TileSweepArgs &a, const double *tri, int num_tiles, int batch, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? tile_launch<kLowerMatvec, true>(dim0, a, M, num_tiles, batch, s) : tile_launch<kLowerMatvec, false>(dim0, a, M, num_tiles, batch, s);
+        case kUpperMatvec: return fma ? tile_launch<kUpperMatvec, true>(dim0, a, M, num_tiles, batch, s) : tile_launch<kUpperMatvec, false>(dim0, a, M, num_tiles, batch, s);
+        case kLowerSolve: return tile_launch<kLowerSolve, false>(dim0, a, M, num_tiles, batch, s);
+        case kUpperSolve: return tile_launch<kUpperSolve, false>(dim0, a, M, num_tiles, batch, s);
+    }
+    return cudaErrorInvalidValue;
+}
 
 template <>
 cudaError_t launch_line_sweep<T>(int mode, bool fma, const LineSweepArgs &a, const double *tri, int batch, cudaStream_t s) {

@@ -43,14 +43,27 @@ __device__ __forceinline__ double mac(double acc, double a, double b) {
 template <int MAXT, int MODE, bool FMA>
 __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M) {
     if constexpr (MODE == kLowerMatvec) {
-        // outputs from the top down: out_k only reads x_j, j <= k, so it may overwrite x_k
+        // Outputs from the top down: out_k only reads x_j, j <= k, so it may overwrite x_k.
+        // Two rows are folded side by side (independent accumulators) to halve the dependent
+        // DADD/DFMA chain a lone warp sees; each row keeps its own ascending-j order.
+        static_assert(MAXT % 2 == 0, "rows are processed in pairs");
 #pragma unroll
-        for (int k = MAXT - 1; k >= 0; --k) {
+        for (int k = MAXT - 1; k >= 1; k -= 2) {
             if (k < t) {
-                double acc = 0.0;
+                double a1 = 0.0, a0 = 0.0;
 #pragma unroll
-                for (int j = 0; j <= k; ++j) acc = mac<FMA>(acc, M.v[k * (k + 1) / 2 + j], x[j]);
-                x[k] = acc;
+                for (int j = 0; j < k; ++j) {
+                    a1 = mac<FMA>(a1, M.v[k * (k + 1) / 2 + j], x[j]);
+                    a0 = mac<FMA>(a0, M.v[(k - 1) * k / 2 + j], x[j]);
+                }
+                a1 = mac<FMA>(a1, M.v[k * (k + 1) / 2 + k], x[k]);
+                x[k] = a1;
+                x[k - 1] = a0;
+            } else if (k - 1 < t) {
+                double a0 = 0.0;
+#pragma unroll
+                for (int j = 0; j < k; ++j) a0 = mac<FMA>(a0, M.v[(k - 1) * k / 2 + j], x[j]);
+                x[k - 1] = a0;
             }
         }
     } else if constexpr (MODE == kUpperMatvec) {
@@ -184,6 +197,86 @@ __global__ void __launch_bounds__(THREADS) k_sweep_fibres(const FibreSweepArgs a
         if (k < t) {
             const int e = __ldg(a.ent + p0 + k).x + lane;
             out[a.perm_out ? a.perm_out[e] : e] = x[k];
+        }
+    }
+}
+
+struct TileSweepArgs {
+    const double *in;
+    double *out;
+    const int32_t *tile_fib;   // tile -> first fibre
+    const int32_t *fib_ptr;    // fibre -> first row (entry of ent)
+    const int32_t *thr_start;  // fibre -> first item
+    const int2 *ent;           // rows: {line element offset, line length}
+    const uint32_t *items;     // element-fibres, per tile sorted by length: row | lane << 16 | t << 24
+    const uint32_t *rows0;     // rows, per tile sorted by length: row | len << 24
+    const int32_t *perm_in;    // colex gather on load (or nullptr)
+    const int32_t *perm_out;   // colex scatter on store (or nullptr)
+    int64_t stride;
+};
+
+// Row-tile sweep along coordinate h >= 1, optionally fused with the coordinate-0 sweep.
+//
+// A tile is a run of consecutive fibres of coordinate h: every fibre is a (a_0, a_h) slice made of
+// <= n+1 contiguous lines.  The CTA copies those lines into shared memory (one warp per line:
+// coalesced <= 248 B runs), row r at r*PAD with PAD odd, then
+//   DIM0: thread <-> row, rows ordered by length   (coordinate 0: stride 1)
+//   always: thread <-> element-fibre (slice, lane a_0), ordered by length (stride PAD)
+// and writes the lines back.  Because the work items are ordered by length on the host, the 32
+// lanes of a warp run triangles of nearly equal size (the unsorted thread<->lane mapping wastes
+// 50-80 % of the FP64 lanes on l^2 sets).  Grid: (tiles, batch).
+template <int MAXT, int MODE, bool FMA, bool DIM0, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sweep_tiles(const TileSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    constexpr int PAD = MAXT + 1;
+    __shared__ double buf[THREADS * PAD];
+    const int f0 = a.tile_fib[blockIdx.x], f1 = a.tile_fib[blockIdx.x + 1];
+    const int r0 = a.fib_ptr[f0], nrows = a.fib_ptr[f1] - r0;
+    const int i0 = a.thr_start[f0], nitems = a.thr_start[f1] - i0;
+    const double *in = a.in + int64_t(blockIdx.y) * a.stride;
+    double *out = a.out + int64_t(blockIdx.y) * a.stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int r = warp; r < nrows; r += THREADS / 32) {
+        const int2 en = __ldg(a.ent + r0 + r);
+        if (lane < en.y) {
+            const int e = en.x + lane;
+            buf[r * PAD + lane] = in[a.perm_in ? a.perm_in[e] : e];
+        }
+    }
+    __syncthreads();
+    if constexpr (DIM0) {
+        if (threadIdx.x < nrows) {
+            const uint32_t d = __ldg(a.rows0 + r0 + threadIdx.x);
+            const int t = int(d >> 24);
+            double *row = buf + int(d & 0xffffu) * PAD;
+            double x[MAXT];
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? row[k] : 0.0;
+            apply_fibre<MAXT, MODE, FMA>(x, t, M);
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k)
+                if (k < t) row[k] = x[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < nitems) {
+        const uint32_t d = __ldg(a.items + i0 + threadIdx.x);
+        const int t = int(d >> 24);
+        double *col = buf + int(d & 0xffffu) * PAD + int((d >> 16) & 0xffu);
+        double x[MAXT];
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? col[k * PAD] : 0.0;
+        apply_fibre<MAXT, MODE, FMA>(x, t, M);
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k)
+            if (k < t) col[k * PAD] = x[k];
+    }
+    __syncthreads();
+    for (int r = warp; r < nrows; r += THREADS / 32) {
+        const int2 en = __ldg(a.ent + r0 + r);
+        if (lane < en.y) {
+            const int e = en.x + lane;
+            out[a.perm_out ? a.perm_out[e] : e] = buf[r * PAD + lane];
         }
     }
 }

@@ -15,6 +15,9 @@ cudaError_t launch_line_sweep(int mode, bool fma, const LineSweepArgs &a, const 
 template <int MAXT>
 cudaError_t launch_fibre_sweep(int mode, bool fma, const FibreSweepArgs &a, const double *tri, int batch, cudaStream_t s);
 
+template <int MAXT>
+cudaError_t launch_tile_sweep(int mode, bool fma, bool dim0, const TileSweepArgs &a, const double *tri, int num_tiles, int batch, cudaStream_t s);
+
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s);
 
 }  // namespace lpfnt

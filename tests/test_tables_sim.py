@@ -75,3 +75,27 @@ def test_index_rejects_bad_sets(built_lib):
     B = np.array([[0, 0], [2, 0]], dtype=np.int64)  # coordinate 0 skips a value
     with pytest.raises(ValueError):
         nat.IndexTables(B, 2)
+
+
+@pytest.mark.parametrize("name", ["c1_d2n10", "d3n12_p1", "d4n8", "d5n5_p1", "d6n4", "d3n6_inf", "d3n12_solve", "c2_d3n20_leja"])
+def test_emulated_tile_passes_match_reference(name, built_lib):
+    """Row-tile pass plan: (coordinate 1 + fused coordinate 0), then coordinates 2.. one pass each."""
+    g = load_case(name)
+    m, n = int(g["m"]), int(g["n"])
+    n1 = n + 1
+    tabs = nat.IndexTables(g["A"].astype(np.int64), n)
+    P = g["P"] if bool(g["colex"]) else None
+    v = g["values"][0]
+    x = v[P] if P is not None else v.copy()
+    if bool(g["precomputation"]):
+        M, mode = U.unpack_lower(g["inv_Vx_lt"], n1), "lower"
+    else:
+        M, mode = U.unpack_lower(g["Vx_lt"], n1), "solve"
+    x = sim.sweep_tiles(x, tabs, 1, M, mode, n1, dim0=True)
+    for h in range(2, m):
+        x = sim.sweep_tiles(x, tabs, h, M, mode, n1, dim0=False)
+    assert np.array_equal(x, g["fnt"][0])
+    i = m - 1
+    D = U.unpack_upper(g["Dx_lt0"], n1)
+    if not np.isinf(float(g["p"])):
+        assert np.array_equal(sim.sweep_tiles(g["fnt"][0], tabs, i, D, "upper", n1, dim0=False), g[f"dx_{i}_1"])
