@@ -96,7 +96,10 @@ enum {
     LPFNT_TAB_TILE_FIB = 7,   /* tiles + 1: tile -> first fibre (a tile = consecutive fibres of h) */
     LPFNT_TAB_TILE_ITEMS = 8, /* #threads uint32: per tile its element-fibres, longest first:
                                  row (relative to the tile) | lane << 16 | length << 24         */
-    LPFNT_TAB_TILE_ROWS0 = 9  /* N_1 uint32: per tile its rows, longest first: row | len << 24   */
+    LPFNT_TAB_TILE_ROWS0 = 9, /* N_1 uint32: per tile its rows, longest first: row | len << 24   */
+    LPFNT_TAB_TILE_ROWPOS = 10, /* N_1 uint16: packed shared-memory offset of every row in its tile  */
+    LPFNT_TAB_TILE_ELEMROW = 11,/* N uint8: row (relative to its tile) of every packed tile element  */
+    LPFNT_TAB_TILE_ELEM = 12    /* tiles + 1: CSR of packed elements per tile                        */
 };
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);
@@ -130,10 +133,11 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
 /* options: "force_generic" (1 = route every op through the unbounded-n fallback kernels),
  *          "trace" (1 = record a CUDA-event pair around every kernel launch),
  *          "use_tiles" (0 = per-coordinate line/fibre kernels instead of the row-tile kernels),
+ *          "use_pipe" (0 = non-persistent row-tile kernels with the permutation fused),
  *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line
- * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4 row-tile sweep, 5 row-tile sweep fused with coordinate 0) and its device time in ms.
+ * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4/5 row-tile sweep (5: fused with coordinate 0), 6/7 pipelined row-tile sweep (7: fused), 8 permutation) and its device time in ms.
  * Synchronises on the recorded events.  *count receives the number of records seen. */
 int lpfnt_plan_trace_read(lpfnt_plan *plan, int max_records, int *labels, float *ms, int *count);
 

@@ -124,8 +124,9 @@ def pinned_free(arr: np.ndarray):
 
 
 (TAB_LINE_OFF, TAB_FIB_PTR, TAB_FIB_ENT, TAB_THR_START, TAB_THR_FIB, TAB_LINE_ALPHA, TAB_LEVEL_SIZE,
- TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0) = range(10)
-_TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_TILE_ITEMS: np.uint32, TAB_TILE_ROWS0: np.uint32}
+ TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0, TAB_TILE_ROWPOS, TAB_TILE_ELEMROW, TAB_TILE_ELEM) = range(13)
+_TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_TILE_ITEMS: np.uint32, TAB_TILE_ROWS0: np.uint32,
+              TAB_TILE_ROWPOS: np.uint16, TAB_TILE_ELEMROW: np.uint8}
 
 
 class IndexTables:

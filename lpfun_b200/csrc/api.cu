@@ -31,6 +31,10 @@ struct DeviceDim {
     int2 *ent = nullptr;
     int32_t *tile_fib = nullptr;
     uint32_t *items = nullptr, *rows0 = nullptr;
+    int4 *tile_rec = nullptr;
+    int32_t *tile_elem = nullptr;
+    uint16_t *row_pos = nullptr;
+    uint8_t *elem_row = nullptr;
     int32_t num_threads = 0, max_lines = 0, num_tiles = 0;
 };
 
@@ -61,6 +65,9 @@ struct lpfnt_plan {
     int64_t table_bytes = 0;
     int force_generic = 0;
     int use_tiles = 1;                       // row-tile kernels (sorted work items, fused coordinate 0)
+    int debug_skip = 0;
+    int use_pipe = 0;                        // persistent cp.async-pipelined variant of the row-tile kernels
+    int num_sms = 148;
     int64_t l2_chunk_bytes = int64_t(32) << 20;  // batched multi-pass transforms run in chunks this large
     // optional per-launch tracing (CUDA events around every kernel launch)
     int trace = 0;
@@ -185,13 +192,13 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
             }
         } else if (tiles) {
             const DeviceDim &d = p->dd[h];
-            TileSweepArgs a{in, out, d.tile_fib, d.fib_ptr, d.thr_start, d.ent, d.items, d.rows0,
-                            gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N};
+            TileSweepArgs a{in, out, d.tile_rec, d.tile_elem, d.ent, d.row_pos, d.elem_row, d.items, d.rows0,
+                            gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, p->debug_skip};
             switch (cap) {
-                case 8: e = launch_tile_sweep<8>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
-                case 16: e = launch_tile_sweep<16>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
-                case 24: e = launch_tile_sweep<24>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
-                default: e = launch_tile_sweep<32>(mode, spec.fma, fuse0, a, tri.data(), d.num_tiles, nb, s); break;
+                case 8: e = launch_tile_sweep<8>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
+                case 16: e = launch_tile_sweep<16>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
+                case 24: e = launch_tile_sweep<24>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
+                default: e = launch_tile_sweep<32>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
             }
         } else {
             if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
@@ -207,6 +214,49 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
         trace_end(p, s);
         p->launches += 1;
         if (e != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    }
+    return LPFNT_OK;
+}
+
+// One pipelined row-tile pass along coordinate h (optionally fused with coordinate 0): src -> dst.
+int launch_pipe(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const double *src, double *dst, int64_t batch, cudaStream_t s) {
+    const int n1 = p->n + 1;
+    const int mode = sweep_mode(spec);
+    const DeviceDim &d = p->dd[h];
+    const int len = std::max(d.max_lines, fuse0 ? p->max_line : 0);
+    const int cap = pick_cap(std::max(len, 1));
+    std::vector<double> tri;
+    repack(spec.packed, n1, spec.kind, cap, tri);
+    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 20)) {
+        const int nb = int(std::min<int64_t>(int64_t(1) << 20, batch - b0));
+        const int64_t units = int64_t(d.num_tiles) * nb;
+        int upc = int((units + 3 * p->num_sms - 1) / (3 * p->num_sms));
+        upc = std::max(1, std::min(upc, kPipeMaxUnits));
+        const int grid = int((units + upc - 1) / upc);
+        PipeArgs a{src + b0 * p->N, dst + b0 * p->N, d.tile_rec, d.ent, d.items, d.rows0, p->N, d.num_tiles, nb, fuse0 ? 1 : 0, upc};
+        cudaError_t e = cudaSuccess;
+        trace_begin(p, (fuse0 ? 700 : 600) + h, s);
+        switch (cap) {
+            case 8: e = launch_tile_pipe<8>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
+            case 16: e = launch_tile_pipe<16>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
+            case 24: e = launch_tile_pipe<24>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
+            default: e = launch_tile_pipe<32>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
+        }
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("pipe kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    }
+    return LPFNT_OK;
+}
+
+int launch_perm(lpfnt_plan *p, const double *src, double *dst, int64_t batch, bool scatter, cudaStream_t s) {
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = int(std::min<int64_t>(65535, batch - b0));
+        trace_begin(p, scatter ? 801 : 800, s);
+        cudaError_t e = launch_permute(src + b0 * p->N, dst + b0 * p->N, p->d_perm, p->N, p->N, nb, scatter, s);
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("permute launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
     }
     return LPFNT_OK;
 }
@@ -237,8 +287,35 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     const int np = int(passes.size());
     const size_t fbytes = size_t(p->N) * sizeof(double);
     int64_t chunk = batch;
-    if (np >= 2 && p->l2_chunk_bytes > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, p->l2_chunk_bytes / int64_t(fbytes)));
     const bool permuting = gather || scatter;
+    bool pipe = !p->force_generic && p->use_tiles && p->use_pipe;
+    for (const Pass &ps : passes)
+        pipe = pipe && ps.h >= 1 && p->dd[ps.h].num_tiles > 0 && pick_cap(std::max(p->dd[ps.h].max_lines, ps.fuse0 ? p->max_line : 0)) > 0;
+    const int nlaunch = np + (pipe ? int(gather) + int(scatter) : 0);
+    if (nlaunch >= 2 && p->l2_chunk_bytes > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, p->l2_chunk_bytes / int64_t(fbytes)));
+
+    if (pipe) {
+        // stand-alone permutation passes + pipelined sweeps; everything after the first launch of a
+        // chunk finds its input in L2
+        const bool need_mid = permuting;  // the permutation passes never run in place
+        double *mid_base = nullptr;
+        if (need_mid) { int rc = ensure_ws(p, 2, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[2]; }
+        for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
+            const int64_t nb = std::min(chunk, batch - b0);
+            const double *cur = in + b0 * p->N;
+            double *cout = out + b0 * p->N;
+            if (gather) { int rc = launch_perm(p, cur, mid_base, nb, false, s); if (rc) return rc; cur = mid_base; }
+            for (int q = 0; q < np; ++q) {
+                double *dst = (q == np - 1 && !scatter) ? cout : (need_mid ? mid_base : cout);
+                int rc = launch_pipe(p, spec, passes[q].h, passes[q].fuse0, cur, dst, nb, s);
+                if (rc) return rc;
+                cur = dst;
+            }
+            if (scatter) { int rc = launch_perm(p, cur, cout, nb, true, s); if (rc) return rc; }
+        }
+        return LPFNT_OK;
+    }
+
     // a permuting pass must not run in place; with >= 2 passes the middle buffer absorbs that
     const bool need_mid = (np == 1) ? (permuting && in == out) : (scatter || (permuting && in == out));
     double *mid_base = nullptr;
@@ -333,6 +410,10 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
     CK(cudaSetDevice(device));
 
     lpfnt_plan *p = new lpfnt_plan();
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->num_sms = prop.multiProcessorCount;
+    }
     p->device = device; p->m = m; p->n = n; p->N = N; p->N1 = hx.N1; p->max_line = hx.max_line;
     const int ts = tri_size(n + 1);
     if (nodes) p->nodes.assign(nodes, nodes + n + 1);
@@ -371,6 +452,15 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
             if ((rc = upload(&d.tile_fib, D.tile_fib.data(), D.tile_fib.size(), p))) return fail(rc);
             if ((rc = upload(&d.items, D.items.data(), D.items.size(), p))) return fail(rc);
             if ((rc = upload(&d.rows0, D.rows0.data(), D.rows0.size(), p))) return fail(rc);
+            std::vector<int4> rec(d.num_tiles);
+            for (int tl = 0; tl < d.num_tiles; ++tl) {
+                const int f0 = D.tile_fib[tl], f1 = D.tile_fib[tl + 1];
+                rec[tl] = make_int4(D.fib_ptr[f0], D.fib_ptr[f1] - D.fib_ptr[f0], D.thr_start[f0], D.thr_start[f1] - D.thr_start[f0]);
+            }
+            if ((rc = upload(&d.tile_rec, rec.data(), rec.size(), p))) return fail(rc);
+            if ((rc = upload(&d.tile_elem, D.tile_elem.data(), D.tile_elem.size(), p))) return fail(rc);
+            if ((rc = upload(&d.row_pos, D.row_pos.data(), D.row_pos.size(), p))) return fail(rc);
+            if ((rc = upload(&d.elem_row, D.elem_row.data(), D.elem_row.size(), p))) return fail(rc);
         }
     }
     if (!hx.line_alpha.empty())
@@ -398,7 +488,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
-        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0);
+        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].elem_row);
     }
     for (int s = 0; s < 3; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -416,7 +506,14 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "debug_skip") == 0) { p->debug_skip = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_tiles") == 0) { p->use_tiles = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_pipe") == 0) {
+        // k_tiles_pipe stages kSweepThreads rows per unit; the tile tables are built for 2*kSweepThreads
+        if (value) { set_error("use_pipe: the pipelined variant is disabled in this build (tile size mismatch)"); return LPFNT_EUNSUPPORTED; }
+        p->use_pipe = 0;
+        return LPFNT_OK;
+    }
     if (std::strcmp(name, "l2_chunk_bytes") == 0) { p->l2_chunk_bytes = value; return LPFNT_OK; }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;

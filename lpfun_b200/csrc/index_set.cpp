@@ -261,22 +261,46 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         if (D.max_lines > 255 || max_line > 255) continue;  // descriptors pack lengths into 8 bits
         D.tile_fib.clear();
         D.tile_fib.push_back(0);
-        int32_t rows = 0, items = 0;
+        int32_t rows = 0, items = 0, elems = 0;
         for (int32_t f = 0; f < D.num_fibres; ++f) {
             const int32_t fr = D.fib_ptr[f + 1] - D.fib_ptr[f];
             const int32_t fi = D.thr_start[f + 1] - D.thr_start[f];
-            if (f > D.tile_fib.back() && (rows + fr > kTileRows || items + fi > kTileItems)) {
+            int32_t fe = 0;
+            for (int32_t r = D.fib_ptr[f]; r < D.fib_ptr[f + 1]; ++r) fe += D.ent[r].len;
+            if (f > D.tile_fib.back() && (rows + fr > kTileRows || items + fi > kTileItems || elems + fe > kTileElems)) {
                 D.tile_fib.push_back(f);
                 rows = 0;
                 items = 0;
+                elems = 0;
             }
             rows += fr;
             items += fi;
+            elems += fe;
         }
         D.tile_fib.push_back(D.num_fibres);
         const int32_t ntiles = static_cast<int32_t>(D.tile_fib.size()) - 1;
         D.items.resize(D.num_threads);
         D.rows0.resize(N1);
+        // packed staging layout: the rows of a tile sit back to back in shared memory; row_pos = packed
+        // offset of each row, elem_row = for every packed element its row (uint8), tile_elem = CSR of
+        // packed elements per tile.  Copies in and out of the tile are then one element per lane.
+        D.row_pos.resize(N1);
+        D.elem_row.resize(N);
+        D.tile_elem.assign(ntiles + 1, 0);
+        {
+            int64_t e = 0;
+            for (int32_t tl = 0; tl < ntiles; ++tl) {
+                D.tile_elem[tl] = static_cast<int32_t>(e);
+                const int32_t ra = D.fib_ptr[D.tile_fib[tl]], rb = D.fib_ptr[D.tile_fib[tl + 1]];
+                int32_t pos = 0;
+                for (int32_t r = ra; r < rb; ++r) {
+                    D.row_pos[r] = static_cast<uint16_t>(pos);
+                    for (int32_t c = 0; c < D.ent[r].len; ++c) D.elem_row[e++] = static_cast<uint8_t>(r - ra);
+                    pos += D.ent[r].len;
+                }
+            }
+            D.tile_elem[ntiles] = static_cast<int32_t>(e);
+        }
         std::vector<uint32_t> tmp;
         for (int32_t tl = 0; tl < ntiles; ++tl) {
             const int32_t f0 = D.tile_fib[tl], f1 = D.tile_fib[tl + 1];
@@ -342,6 +366,9 @@ bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t
     if (what == LPFNT_TAB_TILE_FIB) return set(D.tile_fib.data(), 4, D.tile_fib.size(), int64_t(D.tile_fib.size()));
     if (what == LPFNT_TAB_TILE_ITEMS) return set(D.items.data(), 4, D.items.size(), int64_t(D.items.size()));
     if (what == LPFNT_TAB_TILE_ROWS0) return set(D.rows0.data(), 4, D.rows0.size(), int64_t(D.rows0.size()));
+    if (what == LPFNT_TAB_TILE_ROWPOS) return set(D.row_pos.data(), 2, D.row_pos.size(), int64_t(D.row_pos.size()));
+    if (what == LPFNT_TAB_TILE_ELEMROW) return set(D.elem_row.data(), 1, D.elem_row.size(), int64_t(D.elem_row.size()));
+    if (what == LPFNT_TAB_TILE_ELEM) return set(D.tile_elem.data(), 4, D.tile_elem.size(), int64_t(D.tile_elem.size()));
     return false;
 }
 }  // namespace

@@ -10,8 +10,9 @@ namespace lpfnt {
 
 constexpr int kMaxDim = 12;     // spatial dimensions supported by the fast kernels' line descriptors
 constexpr int kMaxRegT = 32;    // longest fibre held in registers by the unrolled kernels (n+1 <= 32)
-constexpr int kTileRows = 128;  // lines staged in shared memory by one CTA of the tile kernel
-constexpr int kTileItems = 128; // element-fibres per CTA (= threads per CTA)
+constexpr int kTileRows = 256;  // lines staged in shared memory by one CTA of the tile kernels
+constexpr int kTileItems = 256; // element-fibres per CTA (two per thread, 128 threads)
+constexpr int kTileElems = 5888; // packed elements per CTA (46 KB; tables included the tile stays below the 48 KB static limit)
 
 void set_error(const std::string &msg);
 
@@ -35,6 +36,9 @@ struct DimTable {
     std::vector<int32_t> tile_fib;       // num_tiles + 1
     std::vector<uint32_t> items;         // num_threads (indexed like the threads: thr_start[f0] + j)
     std::vector<uint32_t> rows0;         // N_1 (indexed like ent: fib_ptr[f0] + j)
+    std::vector<uint16_t> row_pos;       // N_1: packed shared-memory offset of every row inside its tile
+    std::vector<uint8_t> elem_row;       // N: row (relative to the tile) of every packed element
+    std::vector<int32_t> tile_elem;      // num_tiles + 1: CSR of packed elements
 };
 
 // Host-side index structure derived from the multi-index array A (colex order).

@@ -11,6 +11,10 @@ namespace lpfnt {
 
 namespace {
 constexpr int T = LPFNT_MAXT;
+// shared-memory row pitches instantiated for this capacity: the generic odd pitch T+1 and a
+// tight one for the common degrees (n = 30 -> 31, n = 20 -> 21, n = 10 -> 11)
+constexpr int kPadWide = T + 1;
+constexpr int kPadTight = (T == 32) ? 31 : (T == 24) ? 21 : (T == 16) ? 11 : 7;
 
 template <int MODE, bool FMA>
 cudaError_t line_launch(const LineSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
@@ -24,6 +28,39 @@ cudaError_t fibre_launch(const FibreSweepArgs &a, const PackedTri<T> &M, int bat
     k_sweep_fibres<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
 }
+template <int PAD, int MODE, bool FMA>
+cudaError_t pipe_launch_pad(const PipeArgs &a, const PackedTri<T> &M, int grid, cudaStream_t s) {
+    auto kern = k_tiles_pipe<T, PAD, MODE, FMA, kSweepThreads>;
+    const size_t smem = pipe_smem_bytes(PAD);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, kSweepThreads, smem, s>>>(a, M);
+    return cudaGetLastError();
+}
+template <int MODE, bool FMA>
+cudaError_t pipe_launch(const PipeArgs &a, const PackedTri<T> &M, int max_line, int grid, cudaStream_t s) {
+    if (max_line <= kPadTight) return pipe_launch_pad<kPadTight, MODE, FMA>(a, M, grid, s);
+    return pipe_launch_pad<kPadWide, MODE, FMA>(a, M, grid, s);
+}
+}  // namespace
+
+template <>
+cudaError_t launch_tile_pipe<T>(int mode, bool fma, const PipeArgs &a, const double *tri, int max_line, int grid, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? pipe_launch<kLowerMatvec, true>(a, M, max_line, grid, s) : pipe_launch<kLowerMatvec, false>(a, M, max_line, grid, s);
+        case kUpperMatvec: return fma ? pipe_launch<kUpperMatvec, true>(a, M, max_line, grid, s) : pipe_launch<kUpperMatvec, false>(a, M, max_line, grid, s);
+        case kLowerSolve: return pipe_launch<kLowerSolve, false>(a, M, max_line, grid, s);
+        case kUpperSolve: return pipe_launch<kUpperSolve, false>(a, M, max_line, grid, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <int MODE, bool FMA>
 cudaError_t tile_launch(bool dim0, const TileSweepArgs &a, const PackedTri<T> &M, int num_tiles, int batch, cudaStream_t s) {
     dim3 grid(num_tiles, batch);
@@ -31,10 +68,9 @@ cudaError_t tile_launch(bool dim0, const TileSweepArgs &a, const PackedTri<T> &M
     else k_sweep_tiles<T, MODE, FMA, false, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
 }
-}  // namespace
 
 template <>
-cudaError_t launch_tile_sweep<T>(int mode, bool fma, bool dim0, const TileSweepArgs &a, const double *tri, int num_tiles, int batch, cudaStream_t s) {
+cudaError_t launch_tile_sweep<T>(int mode, bool fma, bool dim0, const TileSweepArgs &a, const double *tri, int max_line, int num_tiles, int batch, cudaStream_t s) {
     PackedTri<T> M;
     std::memcpy(M.v, tri, sizeof(M.v));
     switch (mode) {
@@ -73,6 +109,11 @@ cudaError_t launch_fibre_sweep<T>(int mode, bool fma, const FibreSweepArgs &a, c
 }
 
 #if LPFNT_MAXT == 8
+cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s) {
+    dim3 grid(unsigned((n + 255) / 256), batch);
+    k_permute<<<grid, 256, 0, s>>>(x, y, perm, n, stride, scatter ? 1 : 0);
+    return cudaGetLastError();
+}
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s) {
     dim3 grid((a.num_threads + 127) / 128, batch);
     k_sweep_generic<<<grid, 128, 0, s>>>(a);

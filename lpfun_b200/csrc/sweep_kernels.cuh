@@ -49,7 +49,7 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
         static_assert(MAXT % 2 == 0, "rows are processed in pairs");
 #pragma unroll
         for (int k = MAXT - 1; k >= 1; k -= 2) {
-            if (k < t) {
+            if (k - 1 < t) {  // row k-1 is needed; row k rides along (never stored when k == t)
                 double a1 = 0.0, a0 = 0.0;
 #pragma unroll
                 for (int j = 0; j < k; ++j) {
@@ -58,11 +58,6 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
                 }
                 a1 = mac<FMA>(a1, M.v[k * (k + 1) / 2 + k], x[k]);
                 x[k] = a1;
-                x[k - 1] = a0;
-            } else if (k - 1 < t) {
-                double a0 = 0.0;
-#pragma unroll
-                for (int j = 0; j < k; ++j) a0 = mac<FMA>(a0, M.v[(k - 1) * k / 2 + j], x[j]);
                 x[k - 1] = a0;
             }
         }
@@ -99,6 +94,57 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
                 x[k] = __ddiv_rn(__dsub_rn(x[k], s), M.v[k * (k + 1) / 2 + k]);
             }
         }
+    }
+}
+
+// Two register-resident fibres swept side by side with ONE stream of matrix constants.
+// Measured on B200 (tools/probe.cu): a warp that owns one fibre per lane is limited by the
+// LDCU -> FP64 dependency (about 15 cycles per constant pair), far below the FP64 pipe; two fibres
+// per lane halve the constants per term and double the independent chains.  `t` is the longer of
+// the two lengths (the host pairs neighbours of the length-sorted order, so they differ little);
+// the shorter fibre is zero padded, its surplus rows are computed but never stored.
+template <int MAXT, int MODE, bool FMA>
+__device__ __forceinline__ void apply_fibre2(double (&x)[MAXT], double (&y)[MAXT], const int t, const PackedTri<MAXT> &M) {
+    if constexpr (MODE == kLowerMatvec) {
+        static_assert(MAXT % 2 == 0, "rows are processed in pairs");
+#pragma unroll
+        for (int k = MAXT - 1; k >= 1; k -= 2) {
+            if (k - 1 < t) {
+                double a1 = 0.0, a0 = 0.0, b1 = 0.0, b0 = 0.0;
+#pragma unroll
+                for (int j = 0; j < k; ++j) {
+                    const double m1 = M.v[k * (k + 1) / 2 + j], m0 = M.v[(k - 1) * k / 2 + j];
+                    a1 = mac<FMA>(a1, m1, x[j]);
+                    b1 = mac<FMA>(b1, m1, y[j]);
+                    a0 = mac<FMA>(a0, m0, x[j]);
+                    b0 = mac<FMA>(b0, m0, y[j]);
+                }
+                const double md = M.v[k * (k + 1) / 2 + k];
+                x[k] = mac<FMA>(a1, md, x[k]);
+                y[k] = mac<FMA>(b1, md, y[k]);
+                x[k - 1] = a0;
+                y[k - 1] = b0;
+            }
+        }
+    } else if constexpr (MODE == kUpperMatvec) {
+#pragma unroll
+        for (int j = 0; j < MAXT; ++j) {
+            if (j < t) {
+                const double xj = x[j], yj = y[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) {
+                    const double u = M.v[j * (j + 1) / 2 + k];
+                    x[k] = mac<FMA>(x[k], u, xj);
+                    y[k] = mac<FMA>(y[k], u, yj);
+                }
+                const double ud = M.v[j * (j + 1) / 2 + j];
+                x[j] = mac<FMA>(0.0, ud, xj);
+                y[j] = mac<FMA>(0.0, ud, yj);
+            }
+        }
+    } else {
+        apply_fibre<MAXT, MODE, FMA>(x, t, M);
+        apply_fibre<MAXT, MODE, FMA>(y, t, M);
     }
 }
 
@@ -201,85 +247,284 @@ __global__ void __launch_bounds__(THREADS) k_sweep_fibres(const FibreSweepArgs a
     }
 }
 
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+
 struct TileSweepArgs {
     const double *in;
     double *out;
-    const int32_t *tile_fib;   // tile -> first fibre
-    const int32_t *fib_ptr;    // fibre -> first row (entry of ent)
-    const int32_t *thr_start;  // fibre -> first item
+    const int4 *tile_rec;      // per tile {first row, #rows, first item, #items}
+    const int32_t *tile_elem;  // per tile: first packed element (CSR, tiles + 1)
     const int2 *ent;           // rows: {line element offset, line length}
+    const uint16_t *row_pos;   // rows: packed shared-memory offset inside the tile
+    const uint8_t *elem_row;   // packed elements: row (relative to the tile)
     const uint32_t *items;     // element-fibres, per tile sorted by length: row | lane << 16 | t << 24
     const uint32_t *rows0;     // rows, per tile sorted by length: row | len << 24
     const int32_t *perm_in;    // colex gather on load (or nullptr)
     const int32_t *perm_out;   // colex scatter on store (or nullptr)
     int64_t stride;
+    int32_t debug_skip;        // development switch: 1 = skip the sweeps (times the data movement alone)
 };
+
+constexpr int kTileElemCap = 5888;  // packed elements per tile (host: kTileElems)
 
 // Row-tile sweep along coordinate h >= 1, optionally fused with the coordinate-0 sweep.
 //
 // A tile is a run of consecutive fibres of coordinate h: every fibre is a (a_0, a_h) slice made of
-// <= n+1 contiguous lines.  The CTA copies those lines into shared memory (one warp per line:
-// coalesced <= 248 B runs), row r at r*PAD with PAD odd, then
-//   DIM0: thread <-> row, rows ordered by length   (coordinate 0: stride 1)
-//   always: thread <-> element-fibre (slice, lane a_0), ordered by length (stride PAD)
-// and writes the lines back.  Because the work items are ordered by length on the host, the 32
-// lanes of a warp run triangles of nearly equal size (the unsorted thread<->lane mapping wastes
-// 50-80 % of the FP64 lanes on l^2 sets).  Grid: (tiles, batch).
+// <= n+1 contiguous lines ("rows").  The rows of a tile are staged PACKED (back to back) in shared
+// memory.  Everything is one-element-per-lane work:
+//   copy in   packed element i comes from global  i + delta[row(i)]   (cp.async, all in flight at
+//             once; row(i) from a uint8 map, delta[] = line offset - packed offset, in smem)
+//   DIM0      thread <-> two rows (contiguous runs),          sorted by length
+//   sweep h   thread <-> two element-fibres, element k at pos[row + k] + lane, sorted by length
+//   copy out  the mirror image of copy in.
+// ncu on the earlier row-per-warp copy showed 4.7 issued instructions per element at d=6 (rows of
+// ~10 elements leave 2/3 of a warp idle in every copy instruction); here the copies cost ~0.3.
+// The work items are ordered by length on the host, so the 32 lanes of a warp run triangles of
+// nearly equal size, and each thread owns two NEIGHBOURS of that order (apply_fibre2).  Warp w of
+// CTA b takes chunk (w + b) mod 4 of the sorted list.  Grid: (tiles, batch).
 template <int MAXT, int MODE, bool FMA, bool DIM0, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_sweep_tiles(const TileSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
-    constexpr int PAD = MAXT + 1;
-    __shared__ double buf[THREADS * PAD];
-    const int f0 = a.tile_fib[blockIdx.x], f1 = a.tile_fib[blockIdx.x + 1];
-    const int r0 = a.fib_ptr[f0], nrows = a.fib_ptr[f1] - r0;
-    const int i0 = a.thr_start[f0], nitems = a.thr_start[f1] - i0;
+__global__ void __launch_bounds__(THREADS, 3) k_sweep_tiles(const TileSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    __shared__ __align__(16) double buf[kTileElemCap];
+    __shared__ int sdelta[2 * THREADS];
+    __shared__ uint16_t spos[2 * THREADS];
+    constexpr int NW = THREADS / 32;
+    const int4 tr = __ldg(a.tile_rec + blockIdx.x);  // {first row, #rows, first item, #items}
+    const int r0 = tr.x, nrows = tr.y, i0 = tr.z, nitems = tr.w;
+    const int e0 = __ldg(a.tile_elem + blockIdx.x), nelem = __ldg(a.tile_elem + blockIdx.x + 1) - e0;
     const double *in = a.in + int64_t(blockIdx.y) * a.stride;
     double *out = a.out + int64_t(blockIdx.y) * a.stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int r = warp; r < nrows; r += THREADS / 32) {
+    for (int r = threadIdx.x; r < nrows; r += THREADS) {
         const int2 en = __ldg(a.ent + r0 + r);
-        if (lane < en.y) {
-            const int e = en.x + lane;
-            buf[r * PAD + lane] = in[a.perm_in ? a.perm_in[e] : e];
-        }
+        const int pos = __ldg(a.row_pos + r0 + r);
+        spos[r] = static_cast<uint16_t>(pos);
+        sdelta[r] = en.x - pos;
     }
+    // sorted work-item descriptors of this thread; fetched now, used after the copy
+    const int q = (((warp + blockIdx.x) % NW) << 5) + lane;
+    uint32_t it0 = 0, it1 = 0, rw0 = 0, rw1 = 0;
+    if (2 * q < nitems) it0 = __ldg(a.items + i0 + 2 * q);
+    if (2 * q + 1 < nitems) it1 = __ldg(a.items + i0 + 2 * q + 1);
+    if (DIM0 && 2 * q < nrows) rw0 = __ldg(a.rows0 + r0 + 2 * q);
+    if (DIM0 && 2 * q + 1 < nrows) rw1 = __ldg(a.rows0 + r0 + 2 * q + 1);
     __syncthreads();
+
+    const uint8_t *erow = a.elem_row + e0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nelem; i += THREADS) {
+        int src = i + sdelta[__ldg(erow + i)];
+        if (a.perm_in) src = __ldg(a.perm_in + src);
+        cp_async8(buf + i, in + src);
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+
     if constexpr (DIM0) {
-        if (threadIdx.x < nrows) {
-            const uint32_t d = __ldg(a.rows0 + r0 + threadIdx.x);
-            const int t = int(d >> 24);
-            double *row = buf + int(d & 0xffffu) * PAD;
-            double x[MAXT];
+        if (2 * q < nrows) {
+            const int t0 = int(rw0 >> 24), t1 = int(rw1 >> 24);
+            double *p0 = buf + spos[rw0 & 0xffffu], *p1 = buf + spos[rw1 & 0xffffu];
+            double x[MAXT], y[MAXT];
 #pragma unroll
-            for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? row[k] : 0.0;
-            apply_fibre<MAXT, MODE, FMA>(x, t, M);
+            for (int k = 0; k < MAXT; ++k) {
+                x[k] = (k < t0) ? p0[k] : 0.0;
+                y[k] = (k < t1) ? p1[k] : 0.0;
+            }
+            if (!a.debug_skip) apply_fibre2<MAXT, MODE, FMA>(x, y, t0, M);
 #pragma unroll
-            for (int k = 0; k < MAXT; ++k)
-                if (k < t) row[k] = x[k];
+            for (int k = 0; k < MAXT; ++k) {
+                if (k < t0) p0[k] = x[k];
+                if (k < t1) p1[k] = y[k];
+            }
         }
         __syncthreads();
     }
-    if (threadIdx.x < nitems) {
-        const uint32_t d = __ldg(a.items + i0 + threadIdx.x);
-        const int t = int(d >> 24);
-        double *col = buf + int(d & 0xffffu) * PAD + int((d >> 16) & 0xffu);
-        double x[MAXT];
+    if (2 * q < nitems) {
+        const int t0 = int(it0 >> 24), t1 = int(it1 >> 24);
+        const uint16_t *s0 = spos + (it0 & 0xffffu), *s1 = spos + (it1 & 0xffffu);
+        const int l0 = int((it0 >> 16) & 0xffu), l1 = int((it1 >> 16) & 0xffu);
+        double x[MAXT], y[MAXT];
 #pragma unroll
-        for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? col[k * PAD] : 0.0;
-        apply_fibre<MAXT, MODE, FMA>(x, t, M);
+        for (int k = 0; k < MAXT; ++k) {
+            x[k] = (k < t0) ? buf[s0[k] + l0] : 0.0;
+            y[k] = (k < t1) ? buf[s1[k] + l1] : 0.0;
+        }
+        if (!a.debug_skip) apply_fibre2<MAXT, MODE, FMA>(x, y, t0, M);
 #pragma unroll
-        for (int k = 0; k < MAXT; ++k)
-            if (k < t) col[k * PAD] = x[k];
+        for (int k = 0; k < MAXT; ++k) {
+            if (k < t0) buf[s0[k] + l0] = x[k];
+            if (k < t1) buf[s1[k] + l1] = y[k];
+        }
     }
     __syncthreads();
-    for (int r = warp; r < nrows; r += THREADS / 32) {
-        const int2 en = __ldg(a.ent + r0 + r);
-        if (lane < en.y) {
-            const int e = en.x + lane;
-            out[a.perm_out ? a.perm_out[e] : e] = buf[r * PAD + lane];
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nelem; i += THREADS) {
+        int dst = i + sdelta[__ldg(erow + i)];
+        if (a.perm_out) dst = __ldg(a.perm_out + dst);
+        out[dst] = buf[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent, software-pipelined row-tile sweep (the fast path).
+//
+// Same tiles and sorted work items as k_sweep_tiles, but a CTA walks a contiguous range of
+// work units (tile-major, function-minor) and keeps THREE things in flight:
+//   * the rows of unit i+1 travel global -> shared memory with cp.async (LDGSTS, 8 B per lane,
+//     no register staging) into the second data buffer while unit i is being swept,
+//   * the descriptors (row table, sorted items) of unit i+2 travel into a 3-slot ring,
+//   * the stores of unit i-1 drain.
+// ncu on the non-pipelined kernel showed 36 % of warp time in long-scoreboard stalls on the
+// 3-deep dependent chain tile -> descriptors -> rows, and only ~22 % FP64-pipe activity; here
+// the only exposed global latency is the prologue.  The two sweep phases (coordinate 0 over
+// rows, coordinate h over element-fibres) share ONE copy of the unrolled triangle code (phase
+// loop kept rolled) to halve the instruction footprint (17 % "no instruction" stalls before).
+// ---------------------------------------------------------------------------------------
+struct PipeArgs {
+    const double *in;
+    double *out;
+    const int4 *tile_rec;      // per tile {first row, #rows, first item, #items}
+    const int2 *ent;           // rows: {line element offset, line length}
+    const uint32_t *items;     // row | lane << 16 | t << 24, sorted per tile
+    const uint32_t *rows0;     // row | len << 24, sorted per tile
+    int64_t stride;            // elements per function
+    int32_t num_tiles;
+    int32_t batch;             // functions in this launch
+    int32_t fuse0;             // 1: also sweep coordinate 0 (rows) before coordinate h
+    int32_t units_per_cta;
+};
+
+constexpr int kPipeMaxUnits = 128;
+
+// predicated 8-byte shared-memory accesses on 32-bit shared-window addresses
+__device__ __forceinline__ double lds_pred(unsigned addr, bool p) {
+    double v;
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; mov.f64 %0, 0d0000000000000000; @q ld.shared.f64 %0, [%1]; }"
+                 : "=d"(v) : "r"(addr), "r"(int(p)));
+    return v;
+}
+__device__ __forceinline__ void sts_pred(unsigned addr, double v, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(addr), "d"(v), "r"(int(p)) : "memory");
+}
+
+template <int MAXT, int PAD, int MODE, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_tiles_pipe(const PipeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int pad = PAD;  // shared-memory row pitch in doubles (odd, >= longest line)
+    constexpr int buf_elems = THREADS * pad;
+    double *buf = reinterpret_cast<double *>(smem_raw);                      // [2][THREADS * pad]
+    int2 *srow = reinterpret_cast<int2 *>(buf + 2 * buf_elems);              // [3][THREADS]
+    uint32_t *sitem = reinterpret_cast<uint32_t *>(srow + 3 * THREADS);      // [3][THREADS]
+    uint32_t *srow0 = sitem + 3 * THREADS;                                   // [3][THREADS]
+    int4 *strec = reinterpret_cast<int4 *>(srow0 + 3 * THREADS);             // [kPipeMaxUnits]
+
+    const int64_t total = int64_t(a.num_tiles) * a.batch;
+    const int64_t ubeg = int64_t(blockIdx.x) * a.units_per_cta;
+    const int64_t left = total - ubeg;
+    const int nunits = left < a.units_per_cta ? int(left) : a.units_per_cta;
+    if (nunits <= 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = THREADS / 32;
+
+    for (int u = tid; u < nunits; u += THREADS) strec[u] = __ldg(a.tile_rec + (ubeg + u) / a.batch);
+    __syncthreads();
+
+    auto issue_desc = [&](int u) {  // descriptors of local unit u -> ring slot u % 3
+        const int4 tr = strec[u];
+        const int slot = (u % 3) * THREADS;
+        if (tid < tr.y) {
+            cp_async8(srow + slot + tid, a.ent + tr.x + tid);
+            cp_async4(srow0 + slot + tid, a.rows0 + tr.x + tid);
+        }
+        if (tid < tr.w) cp_async4(sitem + slot + tid, a.items + tr.z + tid);
+    };
+    auto issue_rows = [&](int u) {  // rows of local unit u -> data buffer u % 2 (needs its descriptors)
+        const int4 tr = strec[u];
+        const int2 *rows = srow + (u % 3) * THREADS;
+        double *dst = buf + (u & 1) * buf_elems;
+        const double *src = a.in + ((ubeg + u) % a.batch) * a.stride;
+        for (int r = warp; r < tr.y; r += NW) {
+            const int2 en = rows[r];
+            if (lane < en.y) cp_async8(dst + r * pad + lane, src + en.x + lane);
+        }
+    };
+
+    // prologue: descriptors 0 and 1, then the rows of unit 0
+    issue_desc(0);
+    if (nunits > 1) issue_desc(1);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    issue_rows(0);
+    cp_async_commit();
+
+    for (int u = 0; u < nunits; ++u) {
+        cp_async_wait_all();
+        __syncthreads();  // rows(u), descriptors(u+1) landed; every thread is done with unit u-1
+        if (u + 1 < nunits) issue_rows(u + 1);
+        if (u + 2 < nunits) issue_desc(u + 2);
+        cp_async_commit();
+
+        const int4 tr = strec[u];
+        const int slot = (u % 3) * THREADS;
+        double *cur = buf + (u & 1) * buf_elems;
+        const unsigned cur_s = static_cast<unsigned>(__cvta_generic_to_shared(cur));
+#pragma unroll 1
+        for (int ph = a.fuse0 ? 0 : 1; ph < 2; ++ph) {
+            const int cnt = ph == 0 ? tr.y : tr.w;
+            // one code path for both phases: 32-bit shared addresses, run-time element step
+            double x[MAXT];
+            int t = 0;
+            double *p = cur;
+            if (tid < cnt) {
+                const uint32_t d = ph == 0 ? srow0[slot + tid] : sitem[slot + tid];
+                t = int(d >> 24);
+                p = cur + int(d & 0xffffu) * pad + int((d >> 16) & 0xffu);
+            }
+            if (ph == 0) {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? p[k] : 0.0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? p[k * pad] : 0.0;
+            }
+            apply_fibre<MAXT, MODE, FMA>(x, t, M);  // the only copy of the unrolled triangle
+            if (ph == 0) {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k)
+                    if (k < t) p[k] = x[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k)
+                    if (k < t) p[k * pad] = x[k];
+            }
+            __syncthreads();
+        }
+        {
+            const int2 *rows = srow + slot;
+            double *dst = a.out + ((ubeg + u) % a.batch) * a.stride;
+            for (int r = warp; r < tr.y; r += NW) {
+                const int2 en = rows[r];
+                if (lane < en.y) dst[en.x + lane] = cur[r * pad + lane];
+            }
         }
     }
 }
+
+// Colex permutation as a stand-alone streaming pass (used with the pipelined kernels, where it
+// runs on an L2-resident chunk): gather y[e] = x[perm[e]]  /  scatter y[perm[e]] = x[e].
+__global__ void __launch_bounds__(256) k_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int scatter);
 
 // ---------------------------------------------------------------------------------------
 // Generic fallback for fibres longer than the register kernels support (n + 1 > 32): same
@@ -307,6 +552,16 @@ __device__ __forceinline__ double mac_rt(double acc, double a, double b, int fma
 }
 
 #if defined(LPFNT_MAXT) && LPFNT_MAXT == 8  // defined once, in the MAXT=8 translation unit
+__global__ void __launch_bounds__(256) k_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int scatter) {
+    const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double *xf = x + int64_t(blockIdx.y) * stride;
+    double *yf = y + int64_t(blockIdx.y) * stride;
+    const int64_t q = perm[e];
+    if (scatter) yf[q] = xf[e];
+    else yf[e] = xf[q];
+}
+
 __global__ void __launch_bounds__(128) k_sweep_generic(const GenericArgs a) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.num_threads) return;

@@ -73,45 +73,49 @@ def sweep(x, tabs, h, M, mode, n1):
 
 
 def sweep_tiles(x, tabs, h, M, mode, n1, dim0):
-    """Emulates k_sweep_tiles: per tile the rows go to a padded buffer, an optional sweep along
-    coordinate 0 over the rows (sorted row list), then the sweep along h over the sorted items."""
+    """Emulates k_sweep_tiles: per tile the rows are staged PACKED (back to back), an optional sweep
+    along coordinate 0 over the rows (sorted row list), then the sweep along h over the sorted items;
+    copies in and out go through the element->row map exactly like the kernel."""
     tile_fib = tabs.table(nat.TAB_TILE_FIB, h)
     ptr = tabs.table(nat.TAB_FIB_PTR, h)
     ent = tabs.table(nat.TAB_FIB_ENT, h)
     tstart = tabs.table(nat.TAB_THR_START, h)
     items = tabs.table(nat.TAB_TILE_ITEMS, h)
     rows0 = tabs.table(nat.TAB_TILE_ROWS0, h)
+    row_pos = tabs.table(nat.TAB_TILE_ROWPOS, h).astype(np.int64)
+    elem_row = tabs.table(nat.TAB_TILE_ELEMROW, h).astype(np.int64)
+    tile_elem = tabs.table(nat.TAB_TILE_ELEM, h)
     out = np.full_like(x, np.nan)
-    PAD = n1 + 1
     for tl in range(len(tile_fib) - 1):
         f0, f1 = tile_fib[tl], tile_fib[tl + 1]
         r0, r1 = ptr[f0], ptr[f1]
         i0, i1 = tstart[f0], tstart[f1]
-        R = r1 - r0
-        assert R <= 128 and i1 - i0 <= 128
-        buf = np.zeros((R, PAD))
-        for r in range(R):
-            off, ln = ent[r0 + r]
-            buf[r, :ln] = x[off:off + ln]
+        e0, e1 = tile_elem[tl], tile_elem[tl + 1]
+        R, E = r1 - r0, e1 - e0
+        assert R <= 256 and i1 - i0 <= 256 and E <= 5888
+        pos = row_pos[r0:r1]
+        delta = ent[r0:r1, 0] - pos
+        src = np.arange(E) + delta[elem_row[e0:e1]]
+        buf = x[src].copy()
         if dim0:
             d = rows0[r0:r1]
             rr, tt = (d & 0xFFFF).astype(int), (d >> 24).astype(int)
             assert sorted(rr) == list(range(R)) and np.all(np.diff(tt) <= 0)
-            X = np.where(np.arange(n1)[None, :] < tt[:, None], buf[rr][:, :n1], 0.0)
+            idx = pos[rr][:, None] + np.arange(n1)[None, :]
+            valid = np.arange(n1)[None, :] < tt[:, None]
+            X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
             Y = apply_tri(X, M, mode)
-            for q, (r, t) in enumerate(zip(rr, tt)):
-                buf[r, :t] = Y[q, :t]
+            buf[idx[valid]] = Y[valid]
         d = items[i0:i1]
         rr, ll, tt = (d & 0xFFFF).astype(int), ((d >> 16) & 0xFF).astype(int), (d >> 24).astype(int)
         assert np.all(np.diff(tt) <= 0)
-        X = np.zeros((len(d), n1))
-        for q, (r, l, t) in enumerate(zip(rr, ll, tt)):
-            X[q, :t] = buf[r:r + t, l]
+        kk = np.arange(n1)[None, :]
+        valid = kk < tt[:, None]
+        rowidx = np.where(valid, rr[:, None] + kk, 0)
+        idx = pos[rowidx] + ll[:, None]
+        X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
         Y = apply_tri(X, M, mode)
-        for q, (r, l, t) in enumerate(zip(rr, ll, tt)):
-            buf[r:r + t, l] = Y[q, :t]
-        for r in range(R):
-            off, ln = ent[r0 + r]
-            out[off:off + ln] = buf[r, :ln]
+        buf[idx[valid]] = Y[valid]
+        out[src] = buf
     assert not np.isnan(out).any()
     return out
