@@ -99,7 +99,13 @@ enum {
     LPFNT_TAB_TILE_ROWS0 = 9, /* N_1 uint32: per tile its rows, longest first: row | len << 24   */
     LPFNT_TAB_TILE_ROWPOS = 10, /* N_1 uint16: packed shared-memory offset of every row in its tile  */
     LPFNT_TAB_TILE_ELEMROW = 11,/* N uint8: row (relative to its tile) of every packed tile element  */
-    LPFNT_TAB_TILE_ELEM = 12    /* tiles + 1: CSR of packed elements per tile                        */
+    LPFNT_TAB_TILE_ELEM = 12,   /* tiles + 1: start of each tile in the ELEMROW map (4-byte aligned)  */
+    LPFNT_TAB_TILE_NELEM = 13,  /* tiles: number of packed elements of each tile                     */
+    LPFNT_TAB_SORTED = 14,      /* 2 * #threads int32: element-fibres of coordinate h (h = 0: the lines)
+                                   longest first: {first ent entry | line offset, lane | length << 8} */
+    LPFNT_TAB_GROUPS = 15,      /* 2 * #groups int32: runs of <= 8 consecutive lanes of a fibre, tallest first:
+                                   {first ent entry, lane0 | height << 8 | lanes << 16}               */
+    LPFNT_TAB_LINE_ORDER = 16   /* N_1 int32: lines ordered by length inside every chunk of 128 lines  */
 };
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);

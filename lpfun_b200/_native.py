@@ -124,7 +124,7 @@ def pinned_free(arr: np.ndarray):
 
 
 (TAB_LINE_OFF, TAB_FIB_PTR, TAB_FIB_ENT, TAB_THR_START, TAB_THR_FIB, TAB_LINE_ALPHA, TAB_LEVEL_SIZE,
- TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0, TAB_TILE_ROWPOS, TAB_TILE_ELEMROW, TAB_TILE_ELEM) = range(13)
+ TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0, TAB_TILE_ROWPOS, TAB_TILE_ELEMROW, TAB_TILE_ELEM, TAB_TILE_NELEM, TAB_SORTED, TAB_GROUPS, TAB_LINE_ORDER) = range(17)
 _TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_TILE_ITEMS: np.uint32, TAB_TILE_ROWS0: np.uint32,
               TAB_TILE_ROWPOS: np.uint16, TAB_TILE_ELEMROW: np.uint8}
 
@@ -145,7 +145,7 @@ class IndexTables:
         out = np.empty(cnt, dtype=_TAB_DTYPE.get(what, np.int32))
         if cnt:
             check(lib().lpfnt_index_copy(self._h, what, h, out.ctypes.data))
-        return out.reshape(-1, 2) if what == TAB_FIB_ENT else out
+        return out.reshape(-1, 2) if what in (TAB_FIB_ENT, TAB_SORTED, TAB_GROUPS) else out
 
     def close(self):
         if self._h:

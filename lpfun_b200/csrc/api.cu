@@ -32,8 +32,11 @@ struct DeviceDim {
     int32_t *tile_fib = nullptr;
     uint32_t *items = nullptr, *rows0 = nullptr;
     int4 *tile_rec = nullptr;
-    int32_t *tile_elem = nullptr;
+    int2 *sorted = nullptr, *groups = nullptr;
+    int32_t num_sorted = 0, num_groups = 0;
+    int2 *tile_elem = nullptr;
     uint16_t *row_pos = nullptr;
+    int2 *row_desc = nullptr;
     uint8_t *elem_row = nullptr;
     int32_t num_threads = 0, max_lines = 0, num_tiles = 0;
 };
@@ -50,6 +53,8 @@ struct lpfnt_plan {
     bool has_perm = false;
     // device tables
     int32_t *d_line_off = nullptr, *d_perm = nullptr;
+    int2 *d_sorted0 = nullptr;
+    int32_t *d_line_order = nullptr;
     uint8_t *d_line_alpha = nullptr;
     int64_t *d_A = nullptr;       // only for the generic eval fallback (uploaded lazily)
     double *d_nodes = nullptr, *d_mat = nullptr;  // generic-kernel matrix scratch
@@ -64,11 +69,14 @@ struct lpfnt_plan {
     int64_t launches = 0;
     int64_t table_bytes = 0;
     int force_generic = 0;
-    int use_tiles = 1;                       // row-tile kernels (sorted work items, fused coordinate 0)
+    int use_tiles = 0;                       // row-tile kernels (sorted work items, fused coordinate 0); measured slower than the
+                                             // per-coordinate kernels on B200 so far, kept selectable
     int debug_skip = 0;
+    int use_groups = 1;                      // height-ordered lane groups in the per-coordinate fibre kernel
+    int use_sorted = 0;                      // globally length-sorted per-coordinate kernels (no shared memory)
     int use_pipe = 0;                        // persistent cp.async-pipelined variant of the row-tile kernels
     int num_sms = 148;
-    int64_t l2_chunk_bytes = int64_t(32) << 20;  // batched multi-pass transforms run in chunks this large
+    int64_t l2_chunk_bytes = 0;              // > 0: batched multi-pass transforms run in chunks of this many bytes (L2 reuse)
     // optional per-launch tracing (CUDA events around every kernel launch)
     int trace = 0;
     struct TraceRec { int label; cudaEvent_t a, b; };
@@ -154,7 +162,7 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
     const int n1 = p->n + 1;
     const int mode = sweep_mode(spec);
     const int len = (h == 0) ? p->max_line : std::max(p->dd[h].max_lines, fuse0 ? p->max_line : 0);
-    const bool tiles = h >= 1 && p->use_tiles && p->dd[h].num_tiles > 0;
+    const bool tiles = h >= 1 && p->use_tiles && !p->use_sorted && p->dd[h].num_tiles > 0;
     if (fuse0 && !tiles) { set_error("internal: fused coordinate-0 sweep needs the tile kernel"); return LPFNT_EINVAL; }
     const int cap = p->force_generic ? 0 : pick_cap(std::max(len, 1));
     std::vector<double> tri;
@@ -168,8 +176,21 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
         const double *in = src + b0 * p->N;
         double *out = dst + b0 * p->N;
         cudaError_t e = cudaSuccess;
-        trace_begin(p, (cap == 0 ? 200 : (h == 0 ? 0 : (tiles ? (fuse0 ? 500 : 400) : 100))) + h, s);
-        if (cap == 0) {
+        trace_begin(p, (cap == 0 ? 200 : (p->use_sorted ? 900 : (h == 0 ? 0 : (tiles ? (fuse0 ? 500 : 400) : 100)))) + h, s);
+        const bool sorted_ok = cap != 0 && p->use_sorted && !fuse0 && (h == 0 ? p->d_sorted0 != nullptr : p->dd[h].sorted != nullptr);
+        if (sorted_ok) {
+            const int nit = (h == 0) ? int(p->N1) : p->dd[h].num_sorted;
+            SortedSweepArgs a{in, out, h == 0 ? p->d_sorted0 : p->dd[h].sorted, h == 0 ? nullptr : p->dd[h].ent,
+                              gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, nit};
+            // batched: one CTA per function when it fits, so that the L1 keeps the function resident
+            const int threads = (batch > 1 && nit <= 768) ? 768 : 128;
+            switch (cap) {
+                case 8: e = launch_sorted_sweep<8>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
+                case 16: e = launch_sorted_sweep<16>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
+                case 24: e = launch_sorted_sweep<24>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
+                default: e = launch_sorted_sweep<32>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
+            }
+        } else if (cap == 0) {
             GenericArgs a{};
             a.in = in; a.out = out; a.mat = p->d_mat; a.line_off = p->d_line_off;
             a.perm_in = gather ? p->d_perm : nullptr;
@@ -183,7 +204,7 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
             }
             e = launch_generic_sweep(a, nb, s);
         } else if (h == 0) {
-            LineSweepArgs a{in, out, p->d_line_off, gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, int32_t(p->N1)};
+            LineSweepArgs a{in, out, p->d_line_off, gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->d_line_order, p->N, int32_t(p->N1)};
             switch (cap) {
                 case 8: e = launch_line_sweep<8>(mode, spec.fma, a, tri.data(), nb, s); break;
                 case 16: e = launch_line_sweep<16>(mode, spec.fma, a, tri.data(), nb, s); break;
@@ -203,6 +224,19 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
         } else {
             if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
             const DeviceDim &d = p->dd[h];
+            if (p->use_groups && d.groups) {
+                GroupSweepArgs ga{in, out, d.groups, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups};
+                switch (cap) {
+                    case 8: e = launch_group_sweep<8>(mode, spec.fma, ga, tri.data(), nb, s); break;
+                    case 16: e = launch_group_sweep<16>(mode, spec.fma, ga, tri.data(), nb, s); break;
+                    case 24: e = launch_group_sweep<24>(mode, spec.fma, ga, tri.data(), nb, s); break;
+                    default: e = launch_group_sweep<32>(mode, spec.fma, ga, tri.data(), nb, s); break;
+                }
+                trace_end(p, s);
+                p->launches += 1;
+                if (e != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+                continue;
+            }
             FibreSweepArgs a{in, out, d.thr_fib, d.thr_start, d.fib_ptr, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_threads};
             switch (cap) {
                 case 8: e = launch_fibre_sweep<8>(mode, spec.fma, a, tri.data(), nb, s); break;
@@ -230,17 +264,18 @@ int launch_pipe(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const d
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 20)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 20, batch - b0));
         const int64_t units = int64_t(d.num_tiles) * nb;
-        int upc = int((units + 3 * p->num_sms - 1) / (3 * p->num_sms));
+        int upc = int((units + 2 * p->num_sms - 1) / (2 * p->num_sms));
         upc = std::max(1, std::min(upc, kPipeMaxUnits));
         const int grid = int((units + upc - 1) / upc);
-        PipeArgs a{src + b0 * p->N, dst + b0 * p->N, d.tile_rec, d.ent, d.items, d.rows0, p->N, d.num_tiles, nb, fuse0 ? 1 : 0, upc};
+        PipeArgs a{src + b0 * p->N, dst + b0 * p->N, d.tile_rec, d.tile_elem, d.row_desc, d.elem_row, d.items, d.rows0,
+                   p->N, d.num_tiles, nb, fuse0 ? 1 : 0, upc, p->debug_skip};
         cudaError_t e = cudaSuccess;
         trace_begin(p, (fuse0 ? 700 : 600) + h, s);
         switch (cap) {
-            case 8: e = launch_tile_pipe<8>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
-            case 16: e = launch_tile_pipe<16>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
-            case 24: e = launch_tile_pipe<24>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
-            default: e = launch_tile_pipe<32>(mode, spec.fma, a, tri.data(), p->max_line, grid, s); break;
+            case 8: e = launch_tile_pipe<8>(mode, spec.fma, a, tri.data(), grid, s); break;
+            case 16: e = launch_tile_pipe<16>(mode, spec.fma, a, tri.data(), grid, s); break;
+            case 24: e = launch_tile_pipe<24>(mode, spec.fma, a, tri.data(), grid, s); break;
+            default: e = launch_tile_pipe<32>(mode, spec.fma, a, tri.data(), grid, s); break;
         }
         trace_end(p, s);
         p->launches += 1;
@@ -279,7 +314,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     std::vector<Pass> passes;
     {
         size_t q = 0;
-        const bool can_tile = !p->force_generic && p->use_tiles && p->m >= 2 && p->dd[1].num_tiles > 0 &&
+        const bool can_tile = !p->force_generic && !p->use_sorted && p->use_tiles && p->m >= 2 && p->dd[1].num_tiles > 0 &&
                               pick_cap(std::max(p->max_line, p->dd[1].max_lines)) > 0;
         if (dims.size() >= 2 && dims[0] == 0 && dims[1] == 1 && can_tile) { passes.push_back({1, true}); q = 2; }
         for (; q < dims.size(); ++q) passes.push_back({dims[q], false});
@@ -288,7 +323,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     const size_t fbytes = size_t(p->N) * sizeof(double);
     int64_t chunk = batch;
     const bool permuting = gather || scatter;
-    bool pipe = !p->force_generic && p->use_tiles && p->use_pipe;
+    bool pipe = !p->force_generic && p->use_tiles && p->use_pipe && !p->use_sorted;
     for (const Pass &ps : passes)
         pipe = pipe && ps.h >= 1 && p->dd[ps.h].num_tiles > 0 && pick_cap(std::max(p->dd[ps.h].max_lines, ps.fuse0 ? p->max_line : 0)) > 0;
     const int nlaunch = np + (pipe ? int(gather) + int(scatter) : 0);
@@ -447,6 +482,15 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if ((rc = upload(&d.fib_ptr, D.fib_ptr.data(), D.fib_ptr.size(), p))) return fail(rc);
         static_assert(sizeof(FibEnt) == sizeof(int2), "FibEnt must match int2");
         if ((rc = upload(&d.ent, reinterpret_cast<const int2 *>(D.ent.data()), D.ent.size(), p))) return fail(rc);
+        static_assert(sizeof(SortedItem) == sizeof(int2), "SortedItem must match int2");
+        if (!D.sorted.empty()) {
+            d.num_sorted = int32_t(D.sorted.size());
+            if ((rc = upload(&d.sorted, reinterpret_cast<const int2 *>(D.sorted.data()), D.sorted.size(), p))) return fail(rc);
+        }
+        if (!D.groups.empty()) {
+            d.num_groups = int32_t(D.groups.size());
+            if ((rc = upload(&d.groups, reinterpret_cast<const int2 *>(D.groups.data()), D.groups.size(), p))) return fail(rc);
+        }
         if (!D.tile_fib.empty()) {
             d.num_tiles = int32_t(D.tile_fib.size()) - 1;
             if ((rc = upload(&d.tile_fib, D.tile_fib.data(), D.tile_fib.size(), p))) return fail(rc);
@@ -458,11 +502,23 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
                 rec[tl] = make_int4(D.fib_ptr[f0], D.fib_ptr[f1] - D.fib_ptr[f0], D.thr_start[f0], D.thr_start[f1] - D.thr_start[f0]);
             }
             if ((rc = upload(&d.tile_rec, rec.data(), rec.size(), p))) return fail(rc);
-            if ((rc = upload(&d.tile_elem, D.tile_elem.data(), D.tile_elem.size(), p))) return fail(rc);
+            {
+                std::vector<int2> te(d.num_tiles);
+                for (int tl = 0; tl < d.num_tiles; ++tl) te[tl] = make_int2(D.tile_elem[tl], D.tile_nelem[tl]);
+                if ((rc = upload(&d.tile_elem, te.data(), te.size(), p))) return fail(rc);
+            }
             if ((rc = upload(&d.row_pos, D.row_pos.data(), D.row_pos.size(), p))) return fail(rc);
+            {
+                std::vector<int2> rd(D.ent.size());
+                for (size_t r = 0; r < D.ent.size(); ++r) rd[r] = make_int2(D.ent[r].off - int(D.row_pos[r]), int(D.row_pos[r]));
+                if ((rc = upload(&d.row_desc, rd.data(), rd.size(), p))) return fail(rc);
+            }
             if ((rc = upload(&d.elem_row, D.elem_row.data(), D.elem_row.size(), p))) return fail(rc);
         }
     }
+    if ((rc = upload(&p->d_line_order, hx.line_order.data(), hx.line_order.size(), p))) return fail(rc);
+    if (!hx.sorted0.empty())
+        if ((rc = upload(&p->d_sorted0, reinterpret_cast<const int2 *>(hx.sorted0.data()), hx.sorted0.size(), p))) return fail(rc);
     if (!hx.line_alpha.empty())
         if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
     // the generic eval needs A on the device; keep a host copy when that path can be reached
@@ -484,11 +540,11 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
 int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
+    cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_sorted0); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
-        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].elem_row);
+        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
     }
     for (int s = 0; s < 3; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -506,14 +562,11 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_sorted") == 0) { p->use_sorted = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "debug_skip") == 0) { p->debug_skip = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_tiles") == 0) { p->use_tiles = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_pipe") == 0) {
-        // k_tiles_pipe stages kSweepThreads rows per unit; the tile tables are built for 2*kSweepThreads
-        if (value) { set_error("use_pipe: the pipelined variant is disabled in this build (tile size mismatch)"); return LPFNT_EUNSUPPORTED; }
-        p->use_pipe = 0;
-        return LPFNT_OK;
-    }
+    if (std::strcmp(name, "use_pipe") == 0) { p->use_pipe = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "l2_chunk_bytes") == 0) { p->l2_chunk_bytes = value; return LPFNT_OK; }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;

@@ -285,11 +285,13 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         // offset of each row, elem_row = for every packed element its row (uint8), tile_elem = CSR of
         // packed elements per tile.  Copies in and out of the tile are then one element per lane.
         D.row_pos.resize(N1);
-        D.elem_row.resize(N);
+        D.elem_row.assign(size_t(N) + 4 * size_t(ntiles), 0);  // every tile's map starts 4-byte aligned
         D.tile_elem.assign(ntiles + 1, 0);
+        D.tile_nelem.assign(ntiles, 0);
         {
             int64_t e = 0;
             for (int32_t tl = 0; tl < ntiles; ++tl) {
+                e = (e + 3) & ~int64_t(3);
                 D.tile_elem[tl] = static_cast<int32_t>(e);
                 const int32_t ra = D.fib_ptr[D.tile_fib[tl]], rb = D.fib_ptr[D.tile_fib[tl + 1]];
                 int32_t pos = 0;
@@ -298,8 +300,10 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
                     for (int32_t c = 0; c < D.ent[r].len; ++c) D.elem_row[e++] = static_cast<uint8_t>(r - ra);
                     pos += D.ent[r].len;
                 }
+                D.tile_nelem[tl] = pos;
             }
             D.tile_elem[ntiles] = static_cast<int32_t>(e);
+            D.elem_row.resize(size_t((e + 3) & ~int64_t(3)));
         }
         std::vector<uint32_t> tmp;
         for (int32_t tl = 0; tl < ntiles; ++tl) {
@@ -325,6 +329,67 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
             std::stable_sort(tmp.begin(), tmp.end(), [](uint32_t a, uint32_t b) { return (a >> 24) > (b >> 24); });
             std::copy(tmp.begin(), tmp.end(), D.rows0.begin() + r0);
         }
+    }
+
+    // ---- globally length-sorted element-fibres (k_sweep_sorted): per coordinate h >= 1 the items
+    //      {first entry of the fibre in ent, lane | t << 8}, longest first (stable: neighbours in
+    //      the natural order stay neighbours inside a length class); for coordinate 0 the lines
+    //      {element offset, t}. ----
+    {
+        auto sort_desc = [](std::vector<SortedItem> &v) {
+            std::stable_sort(v.begin(), v.end(), [](const SortedItem &a, const SortedItem &b) { return (a.y >> 8) > (b.y >> 8); });
+        };
+        sorted0.clear();
+        if (max_line <= 255) {
+            sorted0.resize(N1);
+            for (int64_t l = 0; l < N1; ++l) sorted0[l] = SortedItem{line_off[l], (line_off[l + 1] - line_off[l]) << 8};
+            sort_desc(sorted0);
+        }
+        for (int h = 1; h < m; ++h) {
+            DimTable &D = dims[h];
+            D.sorted.clear();
+            if (D.max_lines > 255 || max_line > 255) continue;
+            D.sorted.reserve(D.num_threads);
+            for (int32_t f = 0; f < D.num_fibres; ++f) {
+                const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
+                const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
+                for (int32_t lane = 0; lane < lanes; ++lane) {
+                    int32_t t = 0;
+                    while (t < nl && D.ent[p0 + t].len > lane) ++t;
+                    D.sorted.push_back(SortedItem{p0, lane | (t << 8)});
+                }
+            }
+            sort_desc(D.sorted);
+        }
+    }
+
+    // ---- lane groups (k_sweep_groups): every fibre's lanes are cut into runs of <= kGroupLanes
+    //      consecutive lanes; the runs are ordered by height (longest element-fibre first), so that
+    //      the four runs sharing a warp execute triangles of similar size while every run still reads
+    //      and writes >= 64 contiguous bytes per row. ----
+    for (int h = 1; h < m; ++h) {
+        DimTable &D = dims[h];
+        D.groups.clear();
+        if (D.max_lines > 255 || max_line > 255) continue;
+        for (int32_t f = 0; f < D.num_fibres; ++f) {
+            const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
+            const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
+            for (int32_t l0 = 0; l0 < lanes; l0 += kGroupLanes) {
+                int32_t t = 0;  // height of the group's first (tallest) lane
+                while (t < nl && D.ent[p0 + t].len > l0) ++t;
+                D.groups.push_back(SortedItem{p0, l0 | (t << 8) | (std::min(kGroupLanes, lanes - l0) << 16)});
+            }
+        }
+        std::stable_sort(D.groups.begin(), D.groups.end(), [](const SortedItem &a, const SortedItem &b) { return ((a.y >> 8) & 0xff) > ((b.y >> 8) & 0xff); });
+    }
+    // lines ordered by length inside every chunk of kLineChunk consecutive lines (k_sweep_lines)
+    line_order.resize(N1);
+    for (int64_t c0 = 0; c0 < N1; c0 += kLineChunk) {
+        const int64_t c1 = std::min<int64_t>(N1, c0 + kLineChunk);
+        for (int64_t l = c0; l < c1; ++l) line_order[l] = static_cast<int32_t>(l);
+        std::stable_sort(line_order.begin() + c0, line_order.begin() + c1, [&](int32_t a, int32_t b) {
+            return (line_off[a + 1] - line_off[a]) > (line_off[b + 1] - line_off[b]);
+        });
     }
 
     // ---- line descriptors for eval ----
@@ -357,18 +422,23 @@ bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t
     if (what == LPFNT_TAB_LINE_OFF) return set(x.line_off.data(), 4, x.line_off.size(), int64_t(x.line_off.size()));
     if (what == LPFNT_TAB_LINE_ALPHA) return set(x.line_alpha.data(), 1, x.line_alpha.size(), int64_t(x.line_alpha.size()));
     if (what == LPFNT_TAB_LEVEL_SIZE) return set(x.level_size.data(), 8, x.level_size.size(), int64_t(x.level_size.size()));
+    if (what == LPFNT_TAB_LINE_ORDER) return set(x.line_order.data(), 4, x.line_order.size(), int64_t(x.line_order.size()));
+    if (what == LPFNT_TAB_SORTED && h == 0) return set(x.sorted0.data(), 8, x.sorted0.size(), int64_t(2 * x.sorted0.size()));
     if (h < 1 || h >= x.m) return false;
     const DimTable &D = x.dims[h];
     if (what == LPFNT_TAB_FIB_PTR) return set(D.fib_ptr.data(), 4, D.fib_ptr.size(), int64_t(D.fib_ptr.size()));
     if (what == LPFNT_TAB_FIB_ENT) return set(D.ent.data(), 8, D.ent.size(), int64_t(2 * D.ent.size()));
     if (what == LPFNT_TAB_THR_START) return set(D.thr_start.data(), 4, D.thr_start.size(), int64_t(D.thr_start.size()));
     if (what == LPFNT_TAB_THR_FIB) return set(D.thr_fib.data(), 4, D.thr_fib.size(), int64_t(D.thr_fib.size()));
+    if (what == LPFNT_TAB_SORTED) return set(D.sorted.data(), 8, D.sorted.size(), int64_t(2 * D.sorted.size()));
+    if (what == LPFNT_TAB_GROUPS) return set(D.groups.data(), 8, D.groups.size(), int64_t(2 * D.groups.size()));
     if (what == LPFNT_TAB_TILE_FIB) return set(D.tile_fib.data(), 4, D.tile_fib.size(), int64_t(D.tile_fib.size()));
     if (what == LPFNT_TAB_TILE_ITEMS) return set(D.items.data(), 4, D.items.size(), int64_t(D.items.size()));
     if (what == LPFNT_TAB_TILE_ROWS0) return set(D.rows0.data(), 4, D.rows0.size(), int64_t(D.rows0.size()));
     if (what == LPFNT_TAB_TILE_ROWPOS) return set(D.row_pos.data(), 2, D.row_pos.size(), int64_t(D.row_pos.size()));
     if (what == LPFNT_TAB_TILE_ELEMROW) return set(D.elem_row.data(), 1, D.elem_row.size(), int64_t(D.elem_row.size()));
     if (what == LPFNT_TAB_TILE_ELEM) return set(D.tile_elem.data(), 4, D.tile_elem.size(), int64_t(D.tile_elem.size()));
+    if (what == LPFNT_TAB_TILE_NELEM) return set(D.tile_nelem.data(), 4, D.tile_nelem.size(), int64_t(D.tile_nelem.size()));
     return false;
 }
 }  // namespace

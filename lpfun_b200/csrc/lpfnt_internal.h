@@ -10,11 +10,18 @@ namespace lpfnt {
 
 constexpr int kMaxDim = 12;     // spatial dimensions supported by the fast kernels' line descriptors
 constexpr int kMaxRegT = 32;    // longest fibre held in registers by the unrolled kernels (n+1 <= 32)
+constexpr int kGroupLanes = 8;   // consecutive lanes of a fibre that stay together in k_sweep_groups
+constexpr int kLineChunk = 128;  // lines per CTA of k_sweep_lines
 constexpr int kTileRows = 256;  // lines staged in shared memory by one CTA of the tile kernels
 constexpr int kTileItems = 256; // element-fibres per CTA (two per thread, 128 threads)
-constexpr int kTileElems = 5888; // packed elements per CTA (46 KB; tables included the tile stays below the 48 KB static limit)
+constexpr int kTileElems = 5120; // packed elements per CTA (40 KB; two data buffers + descriptor ring = 110 KB -> 2 CTAs/SM)
 
 void set_error(const std::string &msg);
+
+struct SortedItem {  // globally length-sorted work item: x = first entry in ent (h >= 1) or line offset (h = 0); y = lane | t << 8
+    int32_t x;
+    int32_t y;
+};
 
 struct FibEnt {  // one line of a fibre: element offset of the line start and its length
     int32_t off;
@@ -33,12 +40,15 @@ struct DimTable {
     std::vector<int32_t> thr_fib;        // num_threads, thread -> fibre
     // row tiles (see HostIndex::build): tile -> fibre range; per tile the element-fibres and rows
     // sorted by length.  item = row_rel | lane << 16 | t << 24 ; row0 = row_rel | len << 24
+    std::vector<SortedItem> sorted;      // num_threads: element-fibres, longest first
+    std::vector<SortedItem> groups;      // lane runs {first ent entry, lane0 | t << 8 | lanes << 16}, tallest first
     std::vector<int32_t> tile_fib;       // num_tiles + 1
     std::vector<uint32_t> items;         // num_threads (indexed like the threads: thr_start[f0] + j)
     std::vector<uint32_t> rows0;         // N_1 (indexed like ent: fib_ptr[f0] + j)
     std::vector<uint16_t> row_pos;       // N_1: packed shared-memory offset of every row inside its tile
     std::vector<uint8_t> elem_row;       // N: row (relative to the tile) of every packed element
-    std::vector<int32_t> tile_elem;      // num_tiles + 1: CSR of packed elements
+    std::vector<int32_t> tile_elem;      // num_tiles + 1: start of each tile in elem_row (4-aligned)
+    std::vector<int32_t> tile_nelem;     // num_tiles: packed elements of each tile
 };
 
 // Host-side index structure derived from the multi-index array A (colex order).
@@ -49,6 +59,8 @@ struct HostIndex {
     std::vector<int32_t> line_off;       // N_1 + 1 (cs_T)
     std::vector<int64_t> level_size;     // m + 1: N_0, N_1, ..., N_{m-1}, 1
     std::vector<DimTable> dims;          // index h = 0..m-1 (entry 0 unused)
+    std::vector<SortedItem> sorted0;     // N_1: the lines, longest first (coordinate 0)
+    std::vector<int32_t> line_order;     // N_1: lines ordered by length inside every chunk of kLineChunk
     std::vector<uint8_t> line_alpha;     // N_1 * (m-1): (a_1..a_{m-1}) of every line, for eval (n <= 255)
     // returns false (and sets the error) if A is not a colex-ordered downward-closed set
     bool build(const int64_t *A, int64_t N, int m, int n);

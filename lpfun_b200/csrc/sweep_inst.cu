@@ -28,35 +28,29 @@ cudaError_t fibre_launch(const FibreSweepArgs &a, const PackedTri<T> &M, int bat
     k_sweep_fibres<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
 }
-template <int PAD, int MODE, bool FMA>
-cudaError_t pipe_launch_pad(const PipeArgs &a, const PackedTri<T> &M, int grid, cudaStream_t s) {
-    auto kern = k_tiles_pipe<T, PAD, MODE, FMA, kSweepThreads>;
-    const size_t smem = pipe_smem_bytes(PAD);
+template <int MODE, bool FMA>
+cudaError_t pipe_launch(const PipeArgs &a, const PackedTri<T> &M, int grid, cudaStream_t s) {
+    auto kern = k_tiles_pipe<T, MODE, FMA, kSweepThreads>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPipeSmemBytes));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, kSweepThreads, smem, s>>>(a, M);
+    kern<<<grid, kSweepThreads, kPipeSmemBytes, s>>>(a, M);
     return cudaGetLastError();
-}
-template <int MODE, bool FMA>
-cudaError_t pipe_launch(const PipeArgs &a, const PackedTri<T> &M, int max_line, int grid, cudaStream_t s) {
-    if (max_line <= kPadTight) return pipe_launch_pad<kPadTight, MODE, FMA>(a, M, grid, s);
-    return pipe_launch_pad<kPadWide, MODE, FMA>(a, M, grid, s);
 }
 }  // namespace
 
 template <>
-cudaError_t launch_tile_pipe<T>(int mode, bool fma, const PipeArgs &a, const double *tri, int max_line, int grid, cudaStream_t s) {
+cudaError_t launch_tile_pipe<T>(int mode, bool fma, const PipeArgs &a, const double *tri, int grid, cudaStream_t s) {
     PackedTri<T> M;
     std::memcpy(M.v, tri, sizeof(M.v));
     switch (mode) {
-        case kLowerMatvec: return fma ? pipe_launch<kLowerMatvec, true>(a, M, max_line, grid, s) : pipe_launch<kLowerMatvec, false>(a, M, max_line, grid, s);
-        case kUpperMatvec: return fma ? pipe_launch<kUpperMatvec, true>(a, M, max_line, grid, s) : pipe_launch<kUpperMatvec, false>(a, M, max_line, grid, s);
-        case kLowerSolve: return pipe_launch<kLowerSolve, false>(a, M, max_line, grid, s);
-        case kUpperSolve: return pipe_launch<kUpperSolve, false>(a, M, max_line, grid, s);
+        case kLowerMatvec: return fma ? pipe_launch<kLowerMatvec, true>(a, M, grid, s) : pipe_launch<kLowerMatvec, false>(a, M, grid, s);
+        case kUpperMatvec: return fma ? pipe_launch<kUpperMatvec, true>(a, M, grid, s) : pipe_launch<kUpperMatvec, false>(a, M, grid, s);
+        case kLowerSolve: return pipe_launch<kLowerSolve, false>(a, M, grid, s);
+        case kUpperSolve: return pipe_launch<kUpperSolve, false>(a, M, grid, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -67,6 +61,59 @@ cudaError_t tile_launch(bool dim0, const TileSweepArgs &a, const PackedTri<T> &M
     if (dim0) k_sweep_tiles<T, MODE, FMA, true, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     else k_sweep_tiles<T, MODE, FMA, false, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
+}
+
+namespace {
+template <int MODE, bool FMA, bool DIM0>
+cudaError_t sorted_launch(const SortedSweepArgs &a, const PackedTri<T> &M, int threads, int batch, cudaStream_t s) {
+    if (threads > 256) {
+        dim3 grid((a.num_items + 767) / 768, batch);
+        k_sweep_sorted<T, MODE, FMA, DIM0, 768><<<grid, 768, 0, s>>>(a, M);
+    } else {
+        dim3 grid((a.num_items + 127) / 128, batch);
+        k_sweep_sorted<T, MODE, FMA, DIM0, 128><<<grid, 128, 0, s>>>(a, M);
+    }
+    return cudaGetLastError();
+}
+template <int MODE, bool FMA>
+cudaError_t sorted_launch2(bool dim0, const SortedSweepArgs &a, const PackedTri<T> &M, int threads, int batch, cudaStream_t s) {
+    return dim0 ? sorted_launch<MODE, FMA, true>(a, M, threads, batch, s) : sorted_launch<MODE, FMA, false>(a, M, threads, batch, s);
+}
+}  // namespace
+
+template <>
+cudaError_t launch_sorted_sweep<T>(int mode, bool fma, bool dim0, const SortedSweepArgs &a, const double *tri, int threads, int batch, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? sorted_launch2<kLowerMatvec, true>(dim0, a, M, threads, batch, s) : sorted_launch2<kLowerMatvec, false>(dim0, a, M, threads, batch, s);
+        case kUpperMatvec: return fma ? sorted_launch2<kUpperMatvec, true>(dim0, a, M, threads, batch, s) : sorted_launch2<kUpperMatvec, false>(dim0, a, M, threads, batch, s);
+        case kLowerSolve: return sorted_launch2<kLowerSolve, false>(dim0, a, M, threads, batch, s);
+        case kUpperSolve: return sorted_launch2<kUpperSolve, false>(dim0, a, M, threads, batch, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+namespace {
+template <int MODE, bool FMA>
+cudaError_t group_launch(const GroupSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
+    dim3 grid((8 * int64_t(a.num_groups) + kSweepThreads - 1) / kSweepThreads, batch);
+    k_sweep_groups<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <>
+cudaError_t launch_group_sweep<T>(int mode, bool fma, const GroupSweepArgs &a, const double *tri, int batch, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? group_launch<kLowerMatvec, true>(a, M, batch, s) : group_launch<kLowerMatvec, false>(a, M, batch, s);
+        case kUpperMatvec: return fma ? group_launch<kUpperMatvec, true>(a, M, batch, s) : group_launch<kUpperMatvec, false>(a, M, batch, s);
+        case kLowerSolve: return group_launch<kLowerSolve, false>(a, M, batch, s);
+        case kUpperSolve: return group_launch<kUpperSolve, false>(a, M, batch, s);
+    }
+    return cudaErrorInvalidValue;
 }
 
 template <>

@@ -154,6 +154,7 @@ struct LineSweepArgs {
     const int32_t *line_off;  // N_1 + 1
     const int32_t *perm_in;   // gather: x[e] = in[perm_in[e]]  (or nullptr)
     const int32_t *perm_out;  // scatter: out[perm_out[e]] = y[e] (or nullptr)
+    const int32_t *line_order; // lines ordered by length inside every chunk of blockDim.x lines
     int64_t stride;           // elements between consecutive functions of the batch (= N)
     int32_t num_lines;
 };
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(THREADS) k_sweep_lines(const LineSweepArgs a, 
         for (int i = threadIdx.x; i < cnt; i += THREADS) buf[i] = in[e0 + i];
     }
     __syncthreads();
-    const int l = l0 + threadIdx.x;
-    if (l < l1) {
+    if (l0 + int(threadIdx.x) < l1) {
+        const int l = a.line_order[l0 + threadIdx.x];  // the threadIdx.x-th longest line of the chunk
         const int o = a.line_off[l] - e0;
         const int t = a.line_off[l + 1] - a.line_off[l];
         double x[MAXT];
@@ -263,7 +264,7 @@ struct TileSweepArgs {
     const double *in;
     double *out;
     const int4 *tile_rec;      // per tile {first row, #rows, first item, #items}
-    const int32_t *tile_elem;  // per tile: first packed element (CSR, tiles + 1)
+    const int2 *tile_elem;     // per tile {start in elem_row (multiple of 4), #packed elements}
     const int2 *ent;           // rows: {line element offset, line length}
     const uint16_t *row_pos;   // rows: packed shared-memory offset inside the tile
     const uint8_t *elem_row;   // packed elements: row (relative to the tile)
@@ -275,7 +276,7 @@ struct TileSweepArgs {
     int32_t debug_skip;        // development switch: 1 = skip the sweeps (times the data movement alone)
 };
 
-constexpr int kTileElemCap = 5888;  // packed elements per tile (host: kTileElems)
+constexpr int kTileElemCap = 5120;  // packed elements per tile (host: kTileElems)
 
 // Row-tile sweep along coordinate h >= 1, optionally fused with the coordinate-0 sweep.
 //
@@ -300,11 +301,13 @@ __global__ void __launch_bounds__(THREADS, 3) k_sweep_tiles(const TileSweepArgs 
     constexpr int NW = THREADS / 32;
     const int4 tr = __ldg(a.tile_rec + blockIdx.x);  // {first row, #rows, first item, #items}
     const int r0 = tr.x, nrows = tr.y, i0 = tr.z, nitems = tr.w;
-    const int e0 = __ldg(a.tile_elem + blockIdx.x), nelem = __ldg(a.tile_elem + blockIdx.x + 1) - e0;
+    const int2 te = __ldg(a.tile_elem + blockIdx.x);
+    const int nelem = te.y;
     const double *in = a.in + int64_t(blockIdx.y) * a.stride;
     double *out = a.out + int64_t(blockIdx.y) * a.stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const uint8_t *erow = a.elem_row + te.x;
     for (int r = threadIdx.x; r < nrows; r += THREADS) {
         const int2 en = __ldg(a.ent + r0 + r);
         const int pos = __ldg(a.row_pos + r0 + r);
@@ -320,7 +323,6 @@ __global__ void __launch_bounds__(THREADS, 3) k_sweep_tiles(const TileSweepArgs 
     if (DIM0 && 2 * q + 1 < nrows) rw1 = __ldg(a.rows0 + r0 + 2 * q + 1);
     __syncthreads();
 
-    const uint8_t *erow = a.elem_row + e0;
 #pragma unroll 4
     for (int i = threadIdx.x; i < nelem; i += THREADS) {
         int src = i + sdelta[__ldg(erow + i)];
@@ -379,23 +381,25 @@ __global__ void __launch_bounds__(THREADS, 3) k_sweep_tiles(const TileSweepArgs 
 // ---------------------------------------------------------------------------------------
 // Persistent, software-pipelined row-tile sweep (the fast path).
 //
-// Same tiles and sorted work items as k_sweep_tiles, but a CTA walks a contiguous range of
-// work units (tile-major, function-minor) and keeps THREE things in flight:
-//   * the rows of unit i+1 travel global -> shared memory with cp.async (LDGSTS, 8 B per lane,
-//     no register staging) into the second data buffer while unit i is being swept,
-//   * the descriptors (row table, sorted items) of unit i+2 travel into a 3-slot ring,
-//   * the stores of unit i-1 drain.
-// ncu on the non-pipelined kernel showed 36 % of warp time in long-scoreboard stalls on the
-// 3-deep dependent chain tile -> descriptors -> rows, and only ~22 % FP64-pipe activity; here
-// the only exposed global latency is the prologue.  The two sweep phases (coordinate 0 over
-// rows, coordinate h over element-fibres) share ONE copy of the unrolled triangle code (phase
-// loop kept rolled) to halve the instruction footprint (17 % "no instruction" stalls before).
+// Same packed tiles and length-sorted work items as k_sweep_tiles, but a CTA walks a contiguous
+// range of work units (function-major, tile-minor) and keeps three things in flight:
+//   * the packed elements of unit u+1 travel global -> shared memory (cp.async, one element per
+//     lane, every copy of the tile outstanding at once) into the second data buffer,
+//   * the descriptors of unit u+2 (row table, element->row map, sorted items) travel into a
+//     3-slot ring, so that no thread ever waits on a descriptor -> address -> data chain,
+//   * the stores of unit u-1 drain.
+// Measured motivation: with one tile per CTA lifetime the data movement ALONE ran at 1.7-2.9 TB/s
+// (3 CTAs/SM, each a serial chain of 4-10 exposed global latencies); the sweeps themselves reach
+// 55-67 % of the FP64 pipe only when 8 warps/SM are busy (tools/probe2.cu).  2 CTAs x 4 warps per
+// SM, two fibres per thread.
 // ---------------------------------------------------------------------------------------
 struct PipeArgs {
     const double *in;
     double *out;
     const int4 *tile_rec;      // per tile {first row, #rows, first item, #items}
-    const int2 *ent;           // rows: {line element offset, line length}
+    const int2 *tile_elem;     // per tile {start in elem_row (multiple of 4), #packed elements}
+    const int2 *row_desc;      // rows: {line element offset - packed offset, packed offset}
+    const uint8_t *elem_row;   // packed elements: row (relative to the tile)
     const uint32_t *items;     // row | lane << 16 | t << 24, sorted per tile
     const uint32_t *rows0;     // row | len << 24, sorted per tile
     int64_t stride;            // elements per function
@@ -403,31 +407,30 @@ struct PipeArgs {
     int32_t batch;             // functions in this launch
     int32_t fuse0;             // 1: also sweep coordinate 0 (rows) before coordinate h
     int32_t units_per_cta;
+    int32_t debug_skip;
 };
 
 constexpr int kPipeMaxUnits = 128;
+constexpr int kPipeRows = 256;  // rows / items per tile (host: kTileRows, kTileItems)
 
-// predicated 8-byte shared-memory accesses on 32-bit shared-window addresses
-__device__ __forceinline__ double lds_pred(unsigned addr, bool p) {
-    double v;
-    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; mov.f64 %0, 0d0000000000000000; @q ld.shared.f64 %0, [%1]; }"
-                 : "=d"(v) : "r"(addr), "r"(int(p)));
-    return v;
-}
-__device__ __forceinline__ void sts_pred(unsigned addr, double v, bool p) {
-    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(addr), "d"(v), "r"(int(p)) : "memory");
-}
+// shared-memory carve-up of k_tiles_pipe (bytes)
+constexpr size_t kPipeDataBytes = size_t(2) * kTileElemCap * sizeof(double);
+constexpr size_t kPipeMapBytes = size_t(3) * kTileElemCap;
+constexpr size_t kPipeRowBytes = size_t(3) * kPipeRows * sizeof(int2);
+constexpr size_t kPipeItemBytes = size_t(3) * kPipeRows * sizeof(uint32_t);
+constexpr size_t kPipeRecBytes = size_t(kPipeMaxUnits) * (sizeof(int4) + sizeof(int2));
+constexpr size_t kPipeSmemBytes = kPipeDataBytes + kPipeMapBytes + kPipeRowBytes + 2 * kPipeItemBytes + kPipeRecBytes;
 
-template <int MAXT, int PAD, int MODE, bool FMA, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_tiles_pipe(const PipeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+template <int MAXT, int MODE, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k_tiles_pipe(const PipeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int pad = PAD;  // shared-memory row pitch in doubles (odd, >= longest line)
-    constexpr int buf_elems = THREADS * pad;
-    double *buf = reinterpret_cast<double *>(smem_raw);                      // [2][THREADS * pad]
-    int2 *srow = reinterpret_cast<int2 *>(buf + 2 * buf_elems);              // [3][THREADS]
-    uint32_t *sitem = reinterpret_cast<uint32_t *>(srow + 3 * THREADS);      // [3][THREADS]
-    uint32_t *srow0 = sitem + 3 * THREADS;                                   // [3][THREADS]
-    int4 *strec = reinterpret_cast<int4 *>(srow0 + 3 * THREADS);             // [kPipeMaxUnits]
+    double *data = reinterpret_cast<double *>(smem_raw);                                        // [2][cap]
+    uint8_t *smap = smem_raw + kPipeDataBytes;                                                  // [3][cap]
+    int2 *srow = reinterpret_cast<int2 *>(smap + kPipeMapBytes);                                // [3][256] {delta, pos}
+    uint32_t *sitem = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(srow) + kPipeRowBytes);  // [3][256]
+    uint32_t *srow0 = sitem + 3 * kPipeRows;                                                    // [3][256]
+    int4 *strec = reinterpret_cast<int4 *>(srow0 + 3 * kPipeRows);                              // [units]
+    int2 *stel = reinterpret_cast<int2 *>(strec + kPipeMaxUnits);                               // [units]
 
     const int64_t total = int64_t(a.num_tiles) * a.batch;
     const int64_t ubeg = int64_t(blockIdx.x) * a.units_per_cta;
@@ -437,87 +440,105 @@ __global__ void __launch_bounds__(THREADS) k_tiles_pipe(const PipeArgs a, const 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NW = THREADS / 32;
 
-    for (int u = tid; u < nunits; u += THREADS) strec[u] = __ldg(a.tile_rec + (ubeg + u) / a.batch);
+    for (int u = tid; u < nunits; u += THREADS) {
+        const int tile = int((ubeg + u) % a.num_tiles);
+        strec[u] = __ldg(a.tile_rec + tile);
+        stel[u] = __ldg(a.tile_elem + tile);
+    }
     __syncthreads();
 
     auto issue_desc = [&](int u) {  // descriptors of local unit u -> ring slot u % 3
         const int4 tr = strec[u];
-        const int slot = (u % 3) * THREADS;
-        if (tid < tr.y) {
-            cp_async8(srow + slot + tid, a.ent + tr.x + tid);
-            cp_async4(srow0 + slot + tid, a.rows0 + tr.x + tid);
+        const int2 te = stel[u];
+        const int slot = u % 3;
+        for (int r = tid; r < tr.y; r += THREADS) {
+            cp_async8(srow + slot * kPipeRows + r, a.row_desc + tr.x + r);
+            if (a.fuse0) cp_async4(srow0 + slot * kPipeRows + r, a.rows0 + tr.x + r);
         }
-        if (tid < tr.w) cp_async4(sitem + slot + tid, a.items + tr.z + tid);
+        for (int j = tid; j < tr.w; j += THREADS) cp_async4(sitem + slot * kPipeRows + j, a.items + tr.z + j);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.elem_row + te.x);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smap + slot * kTileElemCap);
+        for (int j = tid; 4 * j < te.y; j += THREADS) cp_async4(dst + j, src + j);
     };
-    auto issue_rows = [&](int u) {  // rows of local unit u -> data buffer u % 2 (needs its descriptors)
-        const int4 tr = strec[u];
-        const int2 *rows = srow + (u % 3) * THREADS;
-        double *dst = buf + (u & 1) * buf_elems;
-        const double *src = a.in + ((ubeg + u) % a.batch) * a.stride;
-        for (int r = warp; r < tr.y; r += NW) {
-            const int2 en = rows[r];
-            if (lane < en.y) cp_async8(dst + r * pad + lane, src + en.x + lane);
-        }
+    auto issue_data = [&](int u) {  // packed elements of local unit u -> data buffer u % 2 (needs its descriptors)
+        const int nelem = stel[u].y;
+        const int2 *rows = srow + (u % 3) * kPipeRows;
+        const uint8_t *map = smap + (u % 3) * kTileElemCap;
+        double *dst = data + (u & 1) * kTileElemCap;
+        const double *src = a.in + ((ubeg + u) / a.num_tiles) * a.stride;
+#pragma unroll 4
+        for (int i = tid; i < nelem; i += THREADS) cp_async8(dst + i, src + (i + rows[map[i]].x));
     };
 
-    // prologue: descriptors 0 and 1, then the rows of unit 0
+    // prologue: descriptors 0 and 1, then the data of unit 0
     issue_desc(0);
     if (nunits > 1) issue_desc(1);
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
-    issue_rows(0);
+    issue_data(0);
     cp_async_commit();
 
     for (int u = 0; u < nunits; ++u) {
         cp_async_wait_all();
-        __syncthreads();  // rows(u), descriptors(u+1) landed; every thread is done with unit u-1
-        if (u + 1 < nunits) issue_rows(u + 1);
+        __syncthreads();  // data(u), descriptors(u+1) landed; every thread is done with unit u-1
+        if (u + 1 < nunits) issue_data(u + 1);
         if (u + 2 < nunits) issue_desc(u + 2);
         cp_async_commit();
 
         const int4 tr = strec[u];
-        const int slot = (u % 3) * THREADS;
-        double *cur = buf + (u & 1) * buf_elems;
-        const unsigned cur_s = static_cast<unsigned>(__cvta_generic_to_shared(cur));
-#pragma unroll 1
-        for (int ph = a.fuse0 ? 0 : 1; ph < 2; ++ph) {
-            const int cnt = ph == 0 ? tr.y : tr.w;
-            // one code path for both phases: 32-bit shared addresses, run-time element step
-            double x[MAXT];
-            int t = 0;
-            double *p = cur;
-            if (tid < cnt) {
-                const uint32_t d = ph == 0 ? srow0[slot + tid] : sitem[slot + tid];
-                t = int(d >> 24);
-                p = cur + int(d & 0xffffu) * pad + int((d >> 16) & 0xffu);
-            }
-            if (ph == 0) {
+        const int nelem = stel[u].y;
+        const int slot = u % 3;
+        double *cur = data + (u & 1) * kTileElemCap;
+        const int2 *rows = srow + slot * kPipeRows;
+        // chunk of the sorted lists for this warp (rotated per unit: long chunks visit every SMSP)
+        const int q = (((warp + u + blockIdx.x) % NW) << 5) + lane;
+        if (a.fuse0) {
+            if (2 * q < tr.y) {
+                const uint32_t d0 = srow0[slot * kPipeRows + 2 * q];
+                const uint32_t d1 = (2 * q + 1 < tr.y) ? srow0[slot * kPipeRows + 2 * q + 1] : 0u;
+                const int t0 = int(d0 >> 24), t1 = int(d1 >> 24);
+                double *p0 = cur + rows[d0 & 0xffffu].y, *p1 = cur + rows[d1 & 0xffffu].y;
+                double x[MAXT], y[MAXT];
 #pragma unroll
-                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? p[k] : 0.0;
-            } else {
+                for (int k = 0; k < MAXT; ++k) {
+                    x[k] = (k < t0) ? p0[k] : 0.0;
+                    y[k] = (k < t1) ? p1[k] : 0.0;
+                }
+                if (!a.debug_skip) apply_fibre2<MAXT, MODE, FMA>(x, y, t0, M);
 #pragma unroll
-                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? p[k * pad] : 0.0;
-            }
-            apply_fibre<MAXT, MODE, FMA>(x, t, M);  // the only copy of the unrolled triangle
-            if (ph == 0) {
-#pragma unroll
-                for (int k = 0; k < MAXT; ++k)
-                    if (k < t) p[k] = x[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < MAXT; ++k)
-                    if (k < t) p[k * pad] = x[k];
+                for (int k = 0; k < MAXT; ++k) {
+                    if (k < t0) p0[k] = x[k];
+                    if (k < t1) p1[k] = y[k];
+                }
             }
             __syncthreads();
         }
-        {
-            const int2 *rows = srow + slot;
-            double *dst = a.out + ((ubeg + u) % a.batch) * a.stride;
-            for (int r = warp; r < tr.y; r += NW) {
-                const int2 en = rows[r];
-                if (lane < en.y) dst[en.x + lane] = cur[r * pad + lane];
+        if (2 * q < tr.w) {
+            const uint32_t d0 = sitem[slot * kPipeRows + 2 * q];
+            const uint32_t d1 = (2 * q + 1 < tr.w) ? sitem[slot * kPipeRows + 2 * q + 1] : 0u;
+            const int t0 = int(d0 >> 24), t1 = int(d1 >> 24);
+            const int2 *s0 = rows + (d0 & 0xffffu), *s1 = rows + (d1 & 0xffffu);
+            const int l0 = int((d0 >> 16) & 0xffu), l1 = int((d1 >> 16) & 0xffu);
+            double x[MAXT], y[MAXT];
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) {
+                x[k] = (k < t0) ? cur[s0[k].y + l0] : 0.0;
+                y[k] = (k < t1) ? cur[s1[k].y + l1] : 0.0;
             }
+            if (!a.debug_skip) apply_fibre2<MAXT, MODE, FMA>(x, y, t0, M);
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) {
+                if (k < t0) cur[s0[k].y + l0] = x[k];
+                if (k < t1) cur[s1[k].y + l1] = y[k];
+            }
+        }
+        __syncthreads();
+        {
+            const uint8_t *map = smap + slot * kTileElemCap;
+            double *dst = a.out + ((ubeg + u) / a.num_tiles) * a.stride;
+#pragma unroll 4
+            for (int i = tid; i < nelem; i += THREADS) dst[i + rows[map[i]].x] = cur[i];
         }
     }
 }
@@ -525,6 +546,114 @@ __global__ void __launch_bounds__(THREADS) k_tiles_pipe(const PipeArgs a, const 
 // Colex permutation as a stand-alone streaming pass (used with the pipelined kernels, where it
 // runs on an L2-resident chunk): gather y[e] = x[perm[e]]  /  scatter y[perm[e]] = x[e].
 __global__ void __launch_bounds__(256) k_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int scatter);
+
+// ---------------------------------------------------------------------------------------
+// Length-sorted sweep straight from global memory: thread j owns the j-th LONGEST element-fibre
+// of coordinate h (h = 0: the j-th longest line).  No shared memory, no barriers: the 32 lanes of
+// a warp run triangles of equal size (the natural lane <-> a_0 mapping keeps only 17 % (d=6) to
+// 50 % (d=3, n=30) of the FP64 lanes busy), at the price of less coalesced 8-byte accesses that
+// the L1 absorbs (neighbours of the natural order stay neighbours inside a length class).
+// Grid: (ceil(items / THREADS), batch).
+// ---------------------------------------------------------------------------------------
+struct SortedSweepArgs {
+    const double *in;
+    double *out;
+    const int2 *sorted;       // {first ent entry (h >= 1) | line offset (h = 0), lane | t << 8}
+    const int2 *ent;          // rows of coordinate h (unused for h = 0)
+    const int32_t *perm_in;
+    const int32_t *perm_out;
+    int64_t stride;
+    int32_t num_items;
+};
+
+template <int MAXT, int MODE, bool FMA, bool DIM0, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sweep_sorted(const SortedSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    const int j = blockIdx.x * THREADS + threadIdx.x;
+    if (j >= a.num_items) return;
+    const double *in = a.in + int64_t(blockIdx.y) * a.stride;
+    double *out = a.out + int64_t(blockIdx.y) * a.stride;
+    const int2 it = __ldg(a.sorted + j);
+    const int t = it.y >> 8, lane = it.y & 0xff;
+    double x[MAXT];
+    if constexpr (DIM0) {
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) {
+            x[k] = 0.0;
+            if (k < t) x[k] = in[a.perm_in ? a.perm_in[it.x + k] : it.x + k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) {
+            x[k] = 0.0;
+            if (k < t) x[k] = in[__ldg(a.ent + it.x + k).x + lane];
+        }
+    }
+    apply_fibre<MAXT, MODE, FMA>(x, t, M);
+    if constexpr (DIM0) {
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k)
+            if (k < t) out[a.perm_out ? a.perm_out[it.x + k] : it.x + k] = x[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) {
+            if (k < t) {
+                const int e = __ldg(a.ent + it.x + k).x + lane;
+                out[a.perm_out ? a.perm_out[e] : e] = x[k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Coordinate h >= 1 with height-ordered lane groups: like k_sweep_fibres, but the unit that
+// stays together is a run of <= 8 consecutive lanes of one fibre (64 contiguous bytes per row),
+// and the runs are ordered by height.  A warp holds four runs of similar height, so the unrolled
+// triangle code is not dragged to the tallest fibre of an arbitrary neighbourhood (the natural
+// order keeps 17 % of the FP64 lanes busy at d=6, n=20).  No shared memory, no barriers.
+// Grid: (ceil(8 * groups / THREADS), batch).
+// ---------------------------------------------------------------------------------------
+struct GroupSweepArgs {
+    const double *in;
+    double *out;
+    const int2 *groups;       // {first ent entry, lane0 | height << 8 | lanes << 16}
+    const int2 *ent;
+    const int32_t *perm_out;
+    int64_t stride;
+    int32_t num_groups;
+};
+
+template <int MAXT, int MODE, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    const int j = blockIdx.x * THREADS + threadIdx.x;
+    const int g = j >> 3, sub = j & 7;
+    if (g >= a.num_groups) return;
+    const int2 gr = __ldg(a.groups + g);
+    if (sub >= ((gr.y >> 16) & 0xff)) return;
+    const double *in = a.in + int64_t(blockIdx.y) * a.stride;
+    double *out = a.out + int64_t(blockIdx.y) * a.stride;
+    const int p0 = gr.x, lane = (gr.y & 0xff) + sub, nl = (gr.y >> 8) & 0xff;  // nl = height of the run's first lane
+    double x[MAXT];
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {
+        x[k] = 0.0;
+        if (k < nl) {
+            const int2 en = __ldg(a.ent + p0 + k);
+            if (en.y > lane) {
+                x[k] = in[en.x + lane];
+                t = k + 1;
+            }
+        }
+    }
+    apply_fibre<MAXT, MODE, FMA>(x, t, M);
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {
+        if (k < t) {
+            const int e = __ldg(a.ent + p0 + k).x + lane;
+            out[a.perm_out ? a.perm_out[e] : e] = x[k];
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // Generic fallback for fibres longer than the register kernels support (n + 1 > 32): same

@@ -22,13 +22,13 @@ cudaError_t launch_tile_sweep(int mode, bool fma, bool dim0, const TileSweepArgs
 inline size_t tile_smem_bytes(int pad) { return size_t(2) * kSweepThreads * pad * sizeof(double); }
 
 template <int MAXT>
-cudaError_t launch_tile_pipe(int mode, bool fma, const PipeArgs &a, const double *tri, int max_line, int grid, cudaStream_t s);
+cudaError_t launch_tile_pipe(int mode, bool fma, const PipeArgs &a, const double *tri, int grid, cudaStream_t s);
 
-// dynamic shared memory of k_tiles_pipe for a row pitch: 2 data buffers, 3 descriptor slots, unit records
-inline size_t pipe_smem_bytes(int pad) {
-    return size_t(2) * kSweepThreads * pad * sizeof(double) + size_t(3) * kSweepThreads * (sizeof(int2) + 2 * sizeof(uint32_t)) +
-           size_t(kPipeMaxUnits) * sizeof(int4);
-}
+template <int MAXT>
+cudaError_t launch_sorted_sweep(int mode, bool fma, bool dim0, const SortedSweepArgs &a, const double *tri, int threads, int batch, cudaStream_t s);
+
+template <int MAXT>
+cudaError_t launch_group_sweep(int mode, bool fma, const GroupSweepArgs &a, const double *tri, int batch, cudaStream_t s);
 
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s);

@@ -85,14 +85,17 @@ def sweep_tiles(x, tabs, h, M, mode, n1, dim0):
     row_pos = tabs.table(nat.TAB_TILE_ROWPOS, h).astype(np.int64)
     elem_row = tabs.table(nat.TAB_TILE_ELEMROW, h).astype(np.int64)
     tile_elem = tabs.table(nat.TAB_TILE_ELEM, h)
+    tile_nelem = tabs.table(nat.TAB_TILE_NELEM, h)
     out = np.full_like(x, np.nan)
     for tl in range(len(tile_fib) - 1):
         f0, f1 = tile_fib[tl], tile_fib[tl + 1]
         r0, r1 = ptr[f0], ptr[f1]
         i0, i1 = tstart[f0], tstart[f1]
-        e0, e1 = tile_elem[tl], tile_elem[tl + 1]
+        e0 = tile_elem[tl]
+        e1 = e0 + tile_nelem[tl]
+        assert e0 % 4 == 0
         R, E = r1 - r0, e1 - e0
-        assert R <= 256 and i1 - i0 <= 256 and E <= 5888
+        assert R <= 256 and i1 - i0 <= 256 and E <= 5120
         pos = row_pos[r0:r1]
         delta = ent[r0:r1, 0] - pos
         src = np.arange(E) + delta[elem_row[e0:e1]]

@@ -13,6 +13,7 @@ ap.add_argument("--batch", type=int, default=1024); ap.add_argument("--iters", t
 ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--flush", action="store_true")
 ap.add_argument("--colex", type=int, default=1); ap.add_argument("--trace", type=int, default=1)
 ap.add_argument("--ops", default="fnt,ifnt")
+ap.add_argument("--check", type=int, default=1, help="compare against the per-coordinate generic-path kernels (bit-exact for fnt)")
 a = ap.parse_args()
 t0 = time.time()
 t = lpfun_b200.Transform(a.m, a.n, report=False, colex_order=bool(a.colex), precompilation=False)
@@ -29,6 +30,15 @@ def step():
     if "dx" in ops: t.dx(y, a.m - 1, 1, out=z)
 for _ in range(3): step()
 torch.cuda.synchronize()
+if a.check and 'fnt' in ops:
+    nb = min(a.batch, 8)
+    got = t.fnt(x[:nb].clone()); gotr = t.ifnt(got)
+    t.set_option('use_tiles', 0); t.set_option('use_sorted', 0); t.set_option('use_pipe', 0)
+    ref = t.fnt(x[:nb].clone()); refr = t.ifnt(ref)
+    t.set_option('use_tiles', 1)
+    for o in a.opt:
+        k_, v_ = o.split('='); t.set_option(k_, int(v_))
+    print('   check vs line/fibre kernels: fnt bit-equal', bool(torch.equal(got, ref)), ' ifnt max rel', float(((gotr-refr).abs().max()/refr.abs().max()).item()))
 ts = []
 for _ in range(a.iters):
     if flush is not None: flush.fill_(1)
