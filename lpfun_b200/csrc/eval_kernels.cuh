@@ -58,15 +58,22 @@ __global__ void __launch_bounds__(THREADS) k_eval_horner(const EvalArgs a, const
         const int off = a.line_off[l];
         const int t = a.line_off[l + 1] - off;
         const double *__restrict__ c = a.coeffs + off;
+        // every coefficient of the line is requested before the first FMA needs one (the loads are
+        // warp-uniform broadcasts); the Horner chain then runs in uniform blocks of four
+        double cv[MAXT];
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) cv[k] = (k < t) ? __ldg(c + k) : 0.0;
         double s[PPT];
 #pragma unroll
         for (int q = 0; q < PPT; ++q) s[q] = 0.0;
 #pragma unroll
-        for (int k = MAXT - 1; k >= 0; --k) {
-            if (k < t) {
-                const double ck = __ldg(c + k);
+        for (int kb = MAXT - 4; kb >= 0; kb -= 4) {
+            if (kb < t) {  // zero padding: s stays 0 until the first real coefficient
 #pragma unroll
-                for (int q = 0; q < PPT; ++q) s[q] = __fma_rn(s[q], d0[q][k], ck);
+                for (int k = kb + 3; k >= kb; --k) {
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) s[q] = __fma_rn(s[q], d0[q][k], cv[k]);
+                }
             }
         }
         // fold the finished line into level 1, and every level that completes with it upward

@@ -296,3 +296,28 @@ def test_c5_dx_eval_vs_oracle(T):
     want = o.eval(g["dx_0_1"], g["x"], pts, 20)
     assert relmax(t.eval(g["dx_0_1"], pts), want) <= TOL_EVAL
     t.close()
+
+
+@pytest.mark.parametrize("opts", [
+    {"use_tiles": 1},
+    {"use_tiles": 1, "use_pipe": 1},
+    {"use_tiles": 1, "l2_chunk_bytes": 200000},
+    {"use_sorted": 1},
+    {"use_groups": 0},
+])
+@pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d6n4", "d2n7_inf", "d3n12_solve", "c4_d3n30"])
+def test_alternative_kernel_families(T, name, opts):
+    """The selectable kernel families (row tiles, pipelined tiles, globally sorted, plain fibre order)
+    must all reproduce the reference bit for bit."""
+    g = load_case(name)
+    t = make(T, g, exact_ifnt=True)
+    for k, v in opts.items():
+        t.set_option(k, v)
+    assert np.array_equal(t.fnt(g["values"]), g["fnt"])
+    assert np.array_equal(t.ifnt(g["fnt"]), g["ifnt"])
+    assert np.array_equal(t.fnt(np.tile(g["rnd"], (5, 1)))[3], g["fnt_rnd"])
+    m = int(g["m"])
+    if not (np.isinf(float(g["p"])) and m > 1):
+        assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
+    assert np.array_equal(t.dxT(g["rnd"], m - 1, 1), g[f"dxT_{m-1}_1"])
+    t.close()
