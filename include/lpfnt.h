@@ -139,7 +139,9 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
 /* options: "force_generic" (1 = route every op through the unbounded-n fallback kernels),
  *          "trace" (1 = record a CUDA-event pair around every kernel launch),
  *          "use_tiles" (0 = per-coordinate line/fibre kernels instead of the row-tile kernels),
- *          "use_pipe" (0 = non-persistent row-tile kernels with the permutation fused),
+ *          "use_pipe" (1 = persistent cp.async-pipelined row-tile kernels), "use_sorted" (1 = globally
+ *          length-sorted per-coordinate kernels), "use_groups" (0 = natural lane order in the fibre kernel),
+ *          "use_whole" (1 = whole-function-in-shared-memory kernel for m <= 3),
  *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line

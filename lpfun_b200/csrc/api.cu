@@ -33,6 +33,7 @@ struct DeviceDim {
     uint32_t *items = nullptr, *rows0 = nullptr;
     int4 *tile_rec = nullptr;
     int2 *sorted = nullptr, *groups = nullptr;
+    uint16_t *ent_off16 = nullptr;           // line offsets in fibre order as uint16 (whole-function kernel, N < 65536)
     int32_t num_sorted = 0, num_groups = 0;
     int2 *tile_elem = nullptr;
     uint16_t *row_pos = nullptr;
@@ -72,6 +73,8 @@ struct lpfnt_plan {
     int use_tiles = 0;                       // row-tile kernels (sorted work items, fused coordinate 0); measured slower than the
                                              // per-coordinate kernels on B200 so far, kept selectable
     int debug_skip = 0;
+    int use_whole = 0;                       // m <= 3: whole function in shared memory, one pass per transform (selectable;
+                                             // measured on par with the per-coordinate kernels at d=3 n=30, slower for tiny N)
     int use_groups = 1;                      // height-ordered lane groups in the per-coordinate fibre kernel
     int use_sorted = 0;                      // globally length-sorted per-coordinate kernels (no shared memory)
     int use_pipe = 0;                        // persistent cp.async-pipelined variant of the row-tile kernels
@@ -296,6 +299,54 @@ int launch_perm(lpfnt_plan *p, const double *src, double *dst, int64_t batch, bo
     return LPFNT_OK;
 }
 
+// Whole-function path (m <= 3, everything of one function in shared memory): one launch per transform.
+bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims) {
+    if (!p->use_whole || p->force_generic || p->m > 3 || int(dims.size()) != p->m) return false;
+    for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
+    if (spec.kind != LPFNT_LOWER) return false;
+    if (p->N >= 65536 || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
+    for (int h = 1; h < p->m; ++h) if (!p->dd[h].sorted || !p->dd[h].ent_off16) return false;
+    return whole_smem_bytes(int(p->N), int(p->N1)) <= size_t(220) * 1024;
+}
+
+int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+    const int n1 = p->n + 1;
+    const int mode = sweep_mode(spec);
+    int len = p->max_line;
+    for (int h = 1; h < p->m; ++h) len = std::max(len, p->dd[h].max_lines);
+    const int cap = pick_cap(std::max(len, 1));
+    std::vector<double> tri;
+    repack(spec.packed, n1, spec.kind, cap, tri);
+    WholeArgs a{};
+    a.in = src; a.out = dst;
+    a.sorted[0] = p->d_sorted0; a.ent_off[0] = nullptr;
+    for (int h = 1; h < p->m; ++h) { a.sorted[h] = p->dd[h].sorted; a.ent_off[h] = p->dd[h].ent_off16; }
+    a.perm_in = gather ? p->d_perm : nullptr;
+    a.perm_out = scatter ? p->d_perm : nullptr;
+    a.n_elem = int(p->N); a.n_lines = int(p->N1); a.m = p->m;
+    const size_t smem = whole_smem_bytes(int(p->N), int(p->N1));
+    const int threads = spec.fma ? 256 : 512;
+    int occ = int(std::min<size_t>((size_t(227) * 1024) / (smem + 1024), size_t(2048 / threads)));
+    occ = std::max(1, std::min(occ, spec.fma ? 2 : 1 + (smem < 100 * 1024)));
+    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
+        const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
+        a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
+        const int grid = int(std::min<int64_t>(nb, int64_t(p->num_sms) * occ));
+        cudaError_t e = cudaSuccess;
+        trace_begin(p, 1000, s);
+        switch (cap) {
+            case 8: e = launch_whole<8>(mode, spec.fma, a, tri.data(), grid, s); break;
+            case 16: e = launch_whole<16>(mode, spec.fma, a, tri.data(), grid, s); break;
+            case 24: e = launch_whole<24>(mode, spec.fma, a, tri.data(), grid, s); break;
+            default: e = launch_whole<32>(mode, spec.fma, a, tri.data(), grid, s); break;
+        }
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("whole-function kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    }
+    return LPFNT_OK;
+}
+
 // Device-resident pipeline: sweeps along `dims` (ascending), optional colex gather on the way
 // in and scatter on the way out.  in/out may alias.
 //
@@ -311,6 +362,10 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     scatter = scatter && p->has_perm;
     if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
+    if (whole_ok(p, spec, dims)) {
+        // in-place is safe: a function is read completely into shared memory before it is written
+        return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s);
+    }
     std::vector<Pass> passes;
     {
         size_t q = 0;
@@ -487,6 +542,11 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
             d.num_sorted = int32_t(D.sorted.size());
             if ((rc = upload(&d.sorted, reinterpret_cast<const int2 *>(D.sorted.data()), D.sorted.size(), p))) return fail(rc);
         }
+        if (N < 65536) {
+            std::vector<uint16_t> eo(D.ent.size());
+            for (size_t r = 0; r < D.ent.size(); ++r) eo[r] = uint16_t(D.ent[r].off);
+            if ((rc = upload(&d.ent_off16, eo.data(), eo.size(), p))) return fail(rc);
+        }
         if (!D.groups.empty()) {
             d.num_groups = int32_t(D.groups.size());
             if ((rc = upload(&d.groups, reinterpret_cast<const int2 *>(D.groups.data()), D.groups.size(), p))) return fail(rc);
@@ -544,7 +604,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
-        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
+        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
     }
     for (int s = 0; s < 3; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -562,6 +622,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_sorted") == 0) { p->use_sorted = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "debug_skip") == 0) { p->debug_skip = value ? 1 : 0; return LPFNT_OK; }

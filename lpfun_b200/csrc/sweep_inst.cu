@@ -116,6 +116,34 @@ cudaError_t launch_group_sweep<T>(int mode, bool fma, const GroupSweepArgs &a, c
     return cudaErrorInvalidValue;
 }
 
+namespace {
+template <int MODE, bool FMA, int ITEMS, int THREADS>
+cudaError_t whole_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, cudaStream_t s) {
+    auto kern = k_whole<T, MODE, FMA, ITEMS, THREADS>;
+    const size_t smem = whole_smem_bytes(a.n_elem, a.n_lines);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, THREADS, smem, s>>>(a, M);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <>
+cudaError_t launch_whole<T>(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    // exact arithmetic: one fibre per thread and many warps; FMA: two fibres per thread share the constants
+    switch (mode) {
+        case kLowerMatvec: return fma ? whole_launch<kLowerMatvec, true, 2, 256>(a, M, grid, s) : whole_launch<kLowerMatvec, false, 1, 512>(a, M, grid, s);
+        case kLowerSolve: return whole_launch<kLowerSolve, false, 1, 512>(a, M, grid, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <>
 cudaError_t launch_tile_sweep<T>(int mode, bool fma, bool dim0, const TileSweepArgs &a, const double *tri, int max_line, int num_tiles, int batch, cudaStream_t s) {
     PackedTri<T> M;

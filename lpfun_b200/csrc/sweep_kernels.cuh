@@ -256,6 +256,10 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -651,6 +655,139 @@ __global__ void __launch_bounds__(THREADS) k_sweep_groups(const GroupSweepArgs a
         if (k < t) {
             const int e = __ldg(a.ent + p0 + k).x + lane;
             out[a.perm_out ? a.perm_out[e] : e] = x[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole-function kernel for m <= 3: ONE pass over HBM per transform.
+//
+// A function of an m <= 3 dimensional space with N <= ~28 000 coefficients (d=3, n=30: 15 216 =
+// 119 KB) fits in the shared memory of one SM.  A persistent CTA walks functions b = blockIdx.x,
+// blockIdx.x + gridDim.x, ...; per function it
+//   1. copies the N values in (cp.async, 16 B per lane; 8 B per lane through the colex permutation),
+//   2. sweeps coordinate 0, 1, (2) IN shared memory -- thread <-> element-fibre(s) in registers, the
+//      items of every coordinate ordered by length (host) so that a warp's lanes run equal
+//      triangles, chunks rotated over the warps per function --,
+//   3. copies the N results out (coalesced; 8 B scatter through the permutation for ifnt).
+// All descriptors (sorted items, per-coordinate row offsets) are loaded ONCE per CTA lifetime, so a
+// function costs one exposed global latency; 16 B/DOF of HBM traffic per transform instead of
+// m x 16 B/DOF.  SMs de-synchronise, so some are always in their copy phase while others compute.
+// ITEMS = fibres per thread and round (2 shares the matrix constants between two fibres: FMA form).
+// ---------------------------------------------------------------------------------------
+struct WholeArgs {
+    const double *in;
+    double *out;
+    const int2 *sorted[3];     // per coordinate: items {first entry in ent_off (h >= 1) | line offset (h = 0), lane | t << 8}
+    const uint16_t *ent_off[3]; // per coordinate h >= 1: line offsets in fibre order (N_1 entries); [0] unused
+    const int32_t *perm_in;    // colex gather on the way in (or nullptr)
+    const int32_t *perm_out;   // colex scatter on the way out (or nullptr)
+    int32_t n_elem;            // N
+    int32_t n_lines;           // N_1 = items per coordinate
+    int32_t m;                 // 1..3
+    int32_t batch;
+};
+
+template <int MAXT, int MODE, bool FMA, int ITEMS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_whole(const WholeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.n_elem, N1 = a.n_lines, m = a.m;
+    const int Npad = (N + 1) & ~1;
+    double *buf = reinterpret_cast<double *>(smem_raw);                    // [Npad]
+    int2 *sitem = reinterpret_cast<int2 *>(buf + Npad);                    // [3][N1]: {eo index | t << 24, element offset added}
+    uint16_t *seo = reinterpret_cast<uint16_t *>(sitem + 3 * N1);          // [32 identity][N1 coordinate 1][N1 coordinate 2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = THREADS / 32;
+
+    // One addressing form for every coordinate: element k of an item sits at seo[p + k] + add.
+    //   coordinate 0 (lines):   p = 0 (identity table), add = line offset
+    //   coordinate h >= 1:      p = 32 + (h-1) N1 + first entry of the fibre, add = lane
+    if (tid < 32) seo[tid] = static_cast<uint16_t>(tid);
+    for (int h = 0; h < m; ++h) {
+        for (int i = tid; i < N1; i += THREADS) {
+            const int2 it = __ldg(a.sorted[h] + i);
+            const int t = it.y >> 8;
+            if (h == 0) sitem[i] = make_int2(t << 24, it.x);
+            else {
+                sitem[h * N1 + i] = make_int2((32 + (h - 1) * N1 + it.x) | (t << 24), it.y & 0xff);
+                seo[32 + (h - 1) * N1 + i] = __ldg(a.ent_off[h] + i);
+            }
+        }
+    }
+    const int rounds = (N1 + THREADS * ITEMS - 1) / (THREADS * ITEMS);
+
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        const double *in = a.in + int64_t(b) * N;
+        double *out = a.out + int64_t(b) * N;
+        __syncthreads();  // previous function fully stored (and the tables above written)
+        if (a.perm_in) {
+#pragma unroll 4
+            for (int i = tid; i < N; i += THREADS) cp_async8(buf + i, in + __ldg(a.perm_in + i));
+        } else if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            for (int i = 2 * tid; i + 1 < N; i += 2 * THREADS) cp_async16(buf + i, in + i);
+            if ((N & 1) && tid == 0) cp_async8(buf + N - 1, in + N - 1);
+        } else {
+#pragma unroll 4
+            for (int i = tid; i < N; i += THREADS) cp_async8(buf + i, in + i);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+
+#pragma unroll 1
+        for (int h = 0; h < m; ++h) {
+            const int2 *items = sitem + h * N1;
+#pragma unroll 1
+            for (int r = 0; r < rounds; ++r) {
+                // slot of this thread in the sorted list: chunks rotate over the warps from function to
+                // function so that the long chunks visit every SM sub-partition
+                // (snake order over the rounds: a warp that drew a long chunk in one round draws a short
+                // one in the next, which keeps the barrier tails short)
+                const int wrot = (warp + b) % NW;
+                const int chunk = r * NW + ((r & 1) ? (NW - 1 - wrot) : wrot);
+                if constexpr (ITEMS == 1) {
+                    const int q = chunk * 32 + lane;
+                    int t = 0, add = 0;
+                    const uint16_t *eo = seo;
+                    if (q < N1) { const int2 it = items[q]; t = int(unsigned(it.x) >> 24); eo = seo + (it.x & 0xffffff); add = it.y; }
+                    double x[MAXT];
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[eo[k] + add] : 0.0;
+                    apply_fibre<MAXT, MODE, FMA>(x, t, M);
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) buf[eo[k] + add] = x[k];
+                } else {
+                    const int q = chunk * 64 + 2 * lane;
+                    int t0 = 0, a0 = 0, t1 = 0, a1 = 0;
+                    const uint16_t *e0 = seo, *e1 = seo;
+                    if (q < N1) { const int2 it = items[q]; t0 = int(unsigned(it.x) >> 24); e0 = seo + (it.x & 0xffffff); a0 = it.y; }
+                    if (q + 1 < N1) { const int2 it = items[q + 1]; t1 = int(unsigned(it.x) >> 24); e1 = seo + (it.x & 0xffffff); a1 = it.y; }
+                    double x[MAXT], y[MAXT];
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k) {
+                        x[k] = (k < t0) ? buf[e0[k] + a0] : 0.0;
+                        y[k] = (k < t1) ? buf[e1[k] + a1] : 0.0;
+                    }
+                    apply_fibre2<MAXT, MODE, FMA>(x, y, t0, M);
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k) {
+                        if (k < t0) buf[e0[k] + a0] = x[k];
+                        if (k < t1) buf[e1[k] + a1] = y[k];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (a.perm_out) {
+#pragma unroll 4
+            for (int i = tid; i < N; i += THREADS) out[__ldg(a.perm_out + i)] = buf[i];
+        } else if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            for (int i = 2 * tid; i + 1 < N; i += 2 * THREADS) *reinterpret_cast<double2 *>(out + i) = *reinterpret_cast<const double2 *>(buf + i);
+            if ((N & 1) && tid == 0) out[N - 1] = buf[N - 1];
+        } else {
+#pragma unroll 4
+            for (int i = tid; i < N; i += THREADS) out[i] = buf[i];
         }
     }
 }

@@ -30,6 +30,13 @@ cudaError_t launch_sorted_sweep(int mode, bool fma, bool dim0, const SortedSweep
 template <int MAXT>
 cudaError_t launch_group_sweep(int mode, bool fma, const GroupSweepArgs &a, const double *tri, int batch, cudaStream_t s);
 
+// whole-function kernel (m <= 3): dynamic shared memory = N doubles + per-coordinate item / offset tables
+inline size_t whole_smem_bytes(int n_elem, int n_lines) {
+    return size_t((n_elem + 1) & ~1) * sizeof(double) + size_t(3) * n_lines * sizeof(int2) + (size_t(32) + 2 * size_t(n_lines)) * sizeof(uint16_t) + 16;
+}
+template <int MAXT>
+cudaError_t launch_whole(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s);
+
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s);
 

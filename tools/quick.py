@@ -33,9 +33,9 @@ torch.cuda.synchronize()
 if a.check and 'fnt' in ops:
     nb = min(a.batch, 8)
     got = t.fnt(x[:nb].clone()); gotr = t.ifnt(got)
-    t.set_option('use_tiles', 0); t.set_option('use_sorted', 0); t.set_option('use_pipe', 0)
+    t.set_option('use_tiles', 0); t.set_option('use_sorted', 0); t.set_option('use_pipe', 0); t.set_option('use_whole', 0)
     ref = t.fnt(x[:nb].clone()); refr = t.ifnt(ref)
-    t.set_option('use_tiles', 1)
+    t.set_option('use_tiles', 0)
     for o in a.opt:
         k_, v_ = o.split('='); t.set_option(k_, int(v_))
     print('   check vs line/fibre kernels: fnt bit-equal', bool(torch.equal(got, ref)), ' ifnt max rel', float(((gotr-refr).abs().max()/refr.abs().max()).item()))
