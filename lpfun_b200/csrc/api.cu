@@ -63,10 +63,10 @@ struct lpfnt_plan {
     std::vector<int64_t> hA;      // kept only when the generic eval may need it
     // host copies of the 1-D operators (reference packing)
     std::vector<double> nodes, Vx_lt, inv_Vx_lt, Dx_ut[3], DxT_lt[3];
-    // workspaces (grown on demand)
-    double *ws[3] = {nullptr, nullptr, nullptr};
-    size_t ws_bytes[3] = {0, 0, 0};
-    cudaStream_t stream = nullptr;  // used by the host-pointer paths
+    // workspaces (grown on demand): two lanes x {staged input, staged output, permutation scratch}
+    double *ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
+    cudaStream_t stream = nullptr, stream2 = nullptr;  // used by the host-pointer paths (two lanes)
     int64_t launches = 0;
     int64_t table_bytes = 0;
     int force_generic = 0;
@@ -357,7 +357,7 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
 struct Pass { int h; bool fuse0; };
 
 int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
-               int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+               int64_t batch, bool gather, bool scatter, cudaStream_t s, int mid_slot = 2) {
     gather = gather && p->has_perm;
     scatter = scatter && p->has_perm;
     if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
@@ -389,7 +389,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
         // chunk finds its input in L2
         const bool need_mid = permuting;  // the permutation passes never run in place
         double *mid_base = nullptr;
-        if (need_mid) { int rc = ensure_ws(p, 2, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[2]; }
+        if (need_mid) { int rc = ensure_ws(p, mid_slot, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[mid_slot]; }
         for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
             const int64_t nb = std::min(chunk, batch - b0);
             const double *cur = in + b0 * p->N;
@@ -409,7 +409,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     // a permuting pass must not run in place; with >= 2 passes the middle buffer absorbs that
     const bool need_mid = (np == 1) ? (permuting && in == out) : (scatter || (permuting && in == out));
     double *mid_base = nullptr;
-    if (need_mid) { int rc = ensure_ws(p, 2, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[2]; }
+    if (need_mid) { int rc = ensure_ws(p, mid_slot, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[mid_slot]; }
     for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
         const int64_t nb = std::min(chunk, batch - b0);
         const double *cin = in + b0 * p->N;
@@ -439,20 +439,31 @@ int run_any(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, 
     if (!spec.packed) { set_error("the plan was created without the matrix this operation needs"); return LPFNT_EINVAL; }
     CK(cudaSetDevice(p->device));
     if (on_device) return run_device(p, spec, dims, in, out, batch, gather, scatter, static_cast<cudaStream_t>(stream));
+    // Host pointers: cut the batch into chunks and run them on two lanes (streams) with their own staging
+    // buffers, so that the H2D copy of chunk i+1 overlaps the sweeps and the D2H copy of chunk i
+    // (PCIe is full duplex; the copies dominate this path by an order of magnitude).
     const size_t fbytes = size_t(p->N) * sizeof(double);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, int64_t((size_t(512) << 20) / fbytes)));
-    int rc = ensure_ws(p, 0, size_t(chunk) * fbytes);
-    if (rc) return rc;
-    rc = ensure_ws(p, 1, size_t(chunk) * fbytes);
-    if (rc) return rc;
-    for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
-        const int64_t nb = std::min(chunk, batch - b0);
-        CK(cudaMemcpyAsync(p->ws[0], in + b0 * p->N, size_t(nb) * fbytes, cudaMemcpyHostToDevice, p->stream));
-        rc = run_device(p, spec, dims, p->ws[0], p->ws[1], nb, gather, scatter, p->stream);
+    int64_t chunk = std::max<int64_t>(1, int64_t((size_t(64) << 20) / fbytes));
+    if (batch < 2 * chunk) chunk = std::max<int64_t>(1, (batch + 1) / 2);
+    const int lanes = batch > chunk ? 2 : 1;
+    for (int l = 0; l < lanes; ++l) {
+        int rc = ensure_ws(p, 3 * l, size_t(chunk) * fbytes);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(out + b0 * p->N, p->ws[1], size_t(nb) * fbytes, cudaMemcpyDeviceToHost, p->stream));
+        rc = ensure_ws(p, 3 * l + 1, size_t(chunk) * fbytes);
+        if (rc) return rc;
+    }
+    int i = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += chunk, ++i) {
+        const int64_t nb = std::min(chunk, batch - b0);
+        const int l = (lanes == 2) ? (i & 1) : 0;
+        cudaStream_t s = l ? p->stream2 : p->stream;
+        CK(cudaMemcpyAsync(p->ws[3 * l], in + b0 * p->N, size_t(nb) * fbytes, cudaMemcpyHostToDevice, s));
+        int rc = run_device(p, spec, dims, p->ws[3 * l], p->ws[3 * l + 1], nb, gather, scatter, s, 3 * l + 2);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out + b0 * p->N, p->ws[3 * l + 1], size_t(nb) * fbytes, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(p->stream));
+    if (lanes == 2) CK(cudaStreamSynchronize(p->stream2));
     return LPFNT_OK;
 }
 
@@ -591,6 +602,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
     }
     {
         cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking);
         if (e != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(LPFNT_ECUDA); }
     }
     *plan = p;
@@ -606,15 +618,18 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
         cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
     }
-    for (int s = 0; s < 3; ++s) cudaFree(p->ws[s]);
+    for (int s = 0; s < 6; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
     delete p;
     return LPFNT_OK;
 }
 
 int64_t lpfnt_plan_device_bytes(const lpfnt_plan *p) {
     if (!p) return 0;
-    return p->table_bytes + int64_t(p->ws_bytes[0] + p->ws_bytes[1] + p->ws_bytes[2]);
+    int64_t b = p->table_bytes;
+    for (int s = 0; s < 6; ++s) b += int64_t(p->ws_bytes[s]);
+    return b;
 }
 int64_t lpfnt_plan_launch_count(const lpfnt_plan *p) { return p ? p->launches : 0; }
 
