@@ -130,6 +130,7 @@ def cpu_roundtrip_rate(m: int, n: int, budget_s: float, max_funcs: int, seed: in
     Returns (GDOF/s, functions timed, seconds, threads)."""
     from oracle import oracle as O
 
+    O.use_all_cores()
     o = O.OracleTransform(m, n, 2.0)
     for h in range(m):
         o.sw.neighbors(h)  # plan build, not timed (the reference builds T/cs_T/e_T in its ctor too)
@@ -176,7 +177,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-LABEL_NAMES = {0: "k_sweep_lines", 1: "k_sweep_groups", 2: "k_sweep_generic", 3: "k_eval_horner", 4: "k_sweep_tiles", 5: "k_sweep_tiles+dim0", 6: "k_tiles_pipe", 7: "k_tiles_pipe+dim0", 8: "k_permute", 9: "k_sweep_sorted", 10: "k_whole"}
+LABEL_NAMES = {0: "k_sweep_lines", 1: "k_sweep_groups", 2: "k_sweep_generic", 3: "k_eval_horner", 4: "k_sweep_tiles", 5: "k_sweep_tiles+dim0", 6: "k_tiles_pipe", 7: "k_tiles_pipe+dim0", 8: "k_permute", 9: "k_sweep_sorted", 10: "k_whole", 11: "k_eval_pad", 12: "k_eval_block"}
 
 
 def summarize_trace(recs):

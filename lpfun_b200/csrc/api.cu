@@ -57,6 +57,11 @@ struct lpfnt_plan {
     int2 *d_sorted0 = nullptr;
     int32_t *d_line_order = nullptr;
     uint8_t *d_line_alpha = nullptr;
+    int2 *d_eval_line = nullptr;
+    int4 *d_eval_block = nullptr;
+    double *d_cpad = nullptr;       // padded coefficient layout of the eval kernel
+    int32_t num_eval_blocks = 0;
+    int use_eval_block = 1;
     int64_t *d_A = nullptr;       // only for the generic eval fallback (uploaded lazily)
     double *d_nodes = nullptr, *d_mat = nullptr;  // generic-kernel matrix scratch
     DeviceDim dd[kMaxDim + 1];
@@ -590,6 +595,14 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
     if ((rc = upload(&p->d_line_order, hx.line_order.data(), hx.line_order.size(), p))) return fail(rc);
     if (!hx.sorted0.empty())
         if ((rc = upload(&p->d_sorted0, reinterpret_cast<const int2 *>(hx.sorted0.data()), hx.sorted0.size(), p))) return fail(rc);
+    if (!hx.eval_block.empty()) {
+        static_assert(sizeof(EvalBlock) == sizeof(int4), "EvalBlock must match int4");
+        if ((rc = upload(&p->d_eval_line, reinterpret_cast<const int2 *>(hx.eval_line.data()), hx.eval_line.size(), p))) return fail(rc);
+        if ((rc = upload(&p->d_eval_block, reinterpret_cast<const int4 *>(hx.eval_block.data()), hx.eval_block.size(), p))) return fail(rc);
+        p->num_eval_blocks = int32_t(hx.eval_block.size());
+        if (cudaMalloc(reinterpret_cast<void **>(&p->d_cpad), sizeof(double) * size_t(hx.eval_padded + 4)) != cudaSuccess) { set_error("cudaMalloc(cpad) failed"); return fail(LPFNT_ENOMEM); }
+        p->table_bytes += int64_t(sizeof(double)) * (hx.eval_padded + 4);
+    }
     if (!hx.line_alpha.empty())
         if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
     // the generic eval needs A on the device; keep a host copy when that path can be reached
@@ -612,6 +625,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
 int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
+    cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
     cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_sorted0); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
@@ -637,6 +651,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_sorted") == 0) { p->use_sorted = value ? 1 : 0; return LPFNT_OK; }
@@ -755,13 +770,29 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
         dc = w; dp = w + p->N; dv = p->ws[1];
     }
     if (fast) {
+        const bool blocked = p->use_eval_block && p->d_eval_block && p->d_cpad && (p->m == 1 || p->d_line_alpha);
+        if (blocked) {
+            EvalPadArgs pa{dc, p->d_cpad, p->d_line_off, p->d_eval_line, int32_t(p->N1)};
+            trace_begin(p, 1100, s);
+            cudaError_t e = launch_eval_pad(pa, s);
+            trace_end(p, s);
+            p->launches += 1;
+            if (e != cudaSuccess) { set_error(std::string("eval pad launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+        }
         // grid.x is 32-bit: chunk very large point sets
         const int64_t step = int64_t(1) << 30;
         for (int64_t q0 = 0; q0 < P; q0 += step) {
             const int64_t np = std::min(step, P - q0);
-            EvalArgs a{dc, dp + q0 * p->m, dv + q0, p->d_line_off, p->d_line_alpha, np, int32_t(p->N1), p->m};
-            trace_begin(p, 300, s);
-            cudaError_t e = launch_eval_horner(a, p->nodes.data(), p->n + 1, s);
+            cudaError_t e;
+            if (blocked) {
+                EvalBlockArgs a{p->d_cpad, dp + q0 * p->m, dv + q0, p->d_eval_block, p->d_eval_line, p->d_line_alpha, np, p->num_eval_blocks, p->m};
+                trace_begin(p, 1200, s);
+                e = launch_eval_block(a, p->nodes.data(), p->n + 1, s);
+            } else {
+                EvalArgs a{dc, dp + q0 * p->m, dv + q0, p->d_line_off, p->d_line_alpha, np, int32_t(p->N1), p->m};
+                trace_begin(p, 300, s);
+                e = launch_eval_horner(a, p->nodes.data(), p->n + 1, s);
+            }
             trace_end(p, s);
             p->launches += 1;
             if (e != cudaSuccess) { set_error(std::string("eval launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }

@@ -108,6 +108,181 @@ __global__ void __launch_bounds__(THREADS) k_eval_horner(const EvalArgs a, const
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Block-staged evaluation (the fast path).  Same nested Horner as k_eval_horner, restructured
+// after ncu showed it latency bound at ~10 % of the FP64 pipe (8 warps/SM at 212 registers, one
+// dependent chain descriptor -> coefficients -> FMA chain -> fold per line):
+//   * the coefficients are first re-laid out with every line padded to a multiple of 4 doubles
+//     (k_eval_pad; zero filled), so a line is a run of aligned 32-byte groups;
+//   * a CTA stages blocks of <= 256 lines (<= 24 KB of padded coefficients + descriptors) in shared
+//     memory with cp.async, double buffered: no global latency on the critical path;
+//   * every thread owns PPT points and runs TWO lines at a time (2 x PPT independent FMA chains);
+//     coefficients come from shared memory as 16-byte broadcasts (one LDS per two coefficients).
+// ---------------------------------------------------------------------------------------
+struct EvalBlockArgs {
+    const double *cpad;        // padded coefficients
+    const double *points;      // P x m
+    double *values;            // P
+    const int4 *blocks;        // {first line, #lines, padded offset, padded size}
+    const int2 *lines;         // {padded offset, t}
+    const uint8_t *line_alpha; // N_1 x (m-1)
+    int64_t num_points;
+    int32_t num_blocks;
+    int32_t m;
+};
+
+constexpr int kEvalLB = 256;    // host: kEvalBlockLines
+constexpr int kEvalCB = 2048;   // host: kEvalBlockElems
+
+struct EvalPadArgs {
+    const double *coeffs;
+    double *cpad;
+    const int32_t *line_off;
+    const int2 *lines;
+    int32_t num_lines;
+};
+
+#ifdef LPFNT_EVAL_TU
+__global__ void __launch_bounds__(128) k_eval_pad(const EvalPadArgs a) {
+    const int l = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (l >= a.num_lines) return;
+    const int off = a.line_off[l], t = a.line_off[l + 1] - off;
+    const int2 ln = a.lines[l];
+    const int tp = (t + 3) & ~3;
+    for (int k = lane; k < tp; k += 32) a.cpad[ln.x + k] = (k < t) ? a.coeffs[off + k] : 0.0;
+}
+#endif
+
+__device__ __forceinline__ void cp_async16_e(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8_e(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async1_e(void *smem_dst, const void *gsrc, int bytes4) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+    (void)bytes4;
+}
+
+template <int MAXT, int PPT, int MM, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
+    __shared__ __align__(16) double scb[2][kEvalCB];
+    __shared__ int2 sln[2][kEvalLB];
+    __shared__ __align__(4) uint8_t sal[2][kEvalLB * (MM - 1) + 4];
+    const int tid = threadIdx.x;
+    const int m = a.m;
+    const int64_t p0 = (int64_t(blockIdx.x) * THREADS + tid) * PPT;
+    double x[PPT][MM], d0[PPT][MAXT], acc[PPT][MM];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int64_t p = min(p0 + q, a.num_points - 1);
+#pragma unroll
+        for (int j = 0; j < MM; ++j) {
+            x[q][j] = (j < m) ? a.points[p * m + j] : 0.0;
+            acc[q][j] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
+    }
+
+    auto issue = [&](int bi) {  // stage block bi into buffer bi & 1
+        const int4 b = a.blocks[bi];
+        const int s = bi & 1;
+        for (int i = tid; 2 * i < b.w; i += THREADS) cp_async16_e(&scb[s][2 * i], a.cpad + b.z + 2 * i);
+        for (int i = tid; i < b.y; i += THREADS) cp_async8_e(&sln[s][i], a.lines + b.x + i);
+        // alpha bytes of the block's lines: (m-1) bytes per line, copied in 4-byte words (the source
+        // offset b.x*(m-1) is made 4-byte aligned by starting a few bytes early)
+        const int64_t a0 = int64_t(b.x) * (m - 1);
+        const int shift = int(a0 & 3);
+        const int nbytes = b.y * (m - 1) + shift;
+        const uint8_t *src = a.line_alpha + (a0 - shift);
+        for (int i = tid; 4 * i < nbytes; i += THREADS) cp_async1_e(&sal[s][4 * i], src + 4 * i, 0);
+        asm volatile("cp.async.commit_group;" ::);
+    };
+
+    issue(a.num_blocks - 1);
+    for (int bi = a.num_blocks - 1; bi >= 0; --bi) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();  // block bi landed; everybody is done with the buffer block bi-1 goes into
+        if (bi > 0) issue(bi - 1);
+        const int4 b = a.blocks[bi];
+        const int s = bi & 1;
+        const int shift = int((int64_t(b.x) * (m - 1)) & 3);
+        const uint8_t *al_base = &sal[s][shift];
+        for (int li = b.y - 1; li >= 0; li -= 2) {
+            const int2 lA = sln[s][li];
+            const int2 lB = (li > 0) ? sln[s][li - 1] : make_int2(lA.x, 0);
+            const double *cA = &scb[s][lA.x - b.z];
+            const double *cB = &scb[s][lB.x - b.z];
+            const int tA = lA.y, tB = lB.y;
+            double sA[PPT], sB[PPT];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) sA[q] = sB[q] = 0.0;
+#pragma unroll
+            for (int kb = MAXT - 4; kb >= 0; kb -= 4) {
+                if (kb < tA) {  // zero padding: the partial sum stays 0 until the first real coefficient
+                    const double2 c01 = *reinterpret_cast<const double2 *>(cA + kb);
+                    const double2 c23 = *reinterpret_cast<const double2 *>(cA + kb + 2);
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        sA[q] = __fma_rn(sA[q], d0[q][kb + 3], c23.y);
+                        sA[q] = __fma_rn(sA[q], d0[q][kb + 2], c23.x);
+                        sA[q] = __fma_rn(sA[q], d0[q][kb + 1], c01.y);
+                        sA[q] = __fma_rn(sA[q], d0[q][kb], c01.x);
+                    }
+                }
+                if (kb < tB) {
+                    const double2 c01 = *reinterpret_cast<const double2 *>(cB + kb);
+                    const double2 c23 = *reinterpret_cast<const double2 *>(cB + kb + 2);
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        sB[q] = __fma_rn(sB[q], d0[q][kb + 3], c23.y);
+                        sB[q] = __fma_rn(sB[q], d0[q][kb + 2], c23.x);
+                        sB[q] = __fma_rn(sB[q], d0[q][kb + 1], c01.y);
+                        sB[q] = __fma_rn(sB[q], d0[q][kb], c01.x);
+                    }
+                }
+            }
+            // fold line A, then line B, into level 1 and every level that completes with them
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                if (which == 1 && li == 0) break;
+                const uint8_t *al = al_base + (li - which) * (m - 1);
+                bool carry = true;
+#pragma unroll
+                for (int j = 1; j < MM; ++j) {
+                    if (j < m && carry) {
+                        const int aj = al[j - 1];
+                        const double nd = nodes.v[aj];
+#pragma unroll
+                        for (int q = 0; q < PPT; ++q) {
+                            const double below = (j == 1) ? (which == 0 ? sA[q] : sB[q]) : acc[q][j - 1];
+                            acc[q][j] = __fma_rn(acc[q][j], x[q][j] - nd, below);
+                            if (j > 1) acc[q][j - 1] = 0.0;
+                        }
+                        carry = (aj == 0);
+                    }
+                }
+                if (m == 1) {
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) acc[q][0] = (which == 0) ? sA[q] : sB[q];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        double v = acc[q][0];
+#pragma unroll
+        for (int j = 1; j < MM; ++j)
+            if (j == m - 1) v = acc[q][j];
+        if (p0 + q < a.num_points) a.values[p0 + q] = v;
+    }
+}
+
 // Fallback without unrolling limits (any n, any m): flat sum in the reference's own order,
 // thread per point, basis table in local memory.  A: int64 (N x m) multi-indices on the device.
 struct EvalGenericArgs {

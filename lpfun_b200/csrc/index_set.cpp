@@ -392,6 +392,38 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         });
     }
 
+    // ---- eval program (k_eval_block): the coefficient vector is re-laid out per call with every line
+    //      padded to a multiple of 4 doubles (32-byte aligned, zero filled), and the lines are cut into
+    //      blocks of <= kEvalBlockLines lines / <= kEvalBlockElems padded doubles that a CTA stages in
+    //      shared memory.  eval_line = {padded offset, t}; eval_block = {first line, #lines, padded
+    //      offset of the block, padded size}. ----
+    eval_line.clear();
+    eval_block.clear();
+    eval_padded = 0;
+    if (n <= 255) {
+        eval_line.resize(N1);
+        int64_t pos = 0;
+        for (int64_t l = 0; l < N1; ++l) {
+            const int32_t t = line_off[l + 1] - line_off[l];
+            eval_line[l] = SortedItem{static_cast<int32_t>(pos), t};
+            pos += (t + 3) & ~3;
+        }
+        eval_padded = pos;
+        int64_t l0 = 0;
+        while (l0 < N1) {
+            int64_t l1 = l0;
+            int64_t sz = 0;
+            while (l1 < N1 && l1 - l0 < kEvalBlockLines) {
+                const int64_t add = ((line_off[l1 + 1] - line_off[l1]) + 3) & ~3;
+                if (sz + add > kEvalBlockElems) break;
+                sz += add;
+                ++l1;
+            }
+            eval_block.push_back(EvalBlock{static_cast<int32_t>(l0), static_cast<int32_t>(l1 - l0), eval_line[l0].x, static_cast<int32_t>(sz)});
+            l0 = l1;
+        }
+    }
+
     // ---- line descriptors for eval ----
     line_alpha.clear();
     if (n <= 255 && m >= 2) {

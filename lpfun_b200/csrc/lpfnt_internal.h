@@ -10,6 +10,8 @@ namespace lpfnt {
 
 constexpr int kMaxDim = 12;     // spatial dimensions supported by the fast kernels' line descriptors
 constexpr int kMaxRegT = 32;    // longest fibre held in registers by the unrolled kernels (n+1 <= 32)
+constexpr int kEvalBlockLines = 256;  // lines per shared-memory block of the eval kernel
+constexpr int kEvalBlockElems = 2048;  // padded doubles per block (16 KB)
 constexpr int kGroupLanes = 8;   // consecutive lanes of a fibre that stay together in k_sweep_groups
 constexpr int kLineChunk = 128;  // lines per CTA of k_sweep_lines
 constexpr int kTileRows = 256;  // lines staged in shared memory by one CTA of the tile kernels
@@ -21,6 +23,10 @@ void set_error(const std::string &msg);
 struct SortedItem {  // globally length-sorted work item: x = first entry in ent (h >= 1) or line offset (h = 0); y = lane | t << 8
     int32_t x;
     int32_t y;
+};
+
+struct EvalBlock {  // {first line, #lines, padded offset of the block, padded size in doubles}
+    int32_t l0, nl, poff, npad;
 };
 
 struct FibEnt {  // one line of a fibre: element offset of the line start and its length
@@ -61,6 +67,9 @@ struct HostIndex {
     std::vector<DimTable> dims;          // index h = 0..m-1 (entry 0 unused)
     std::vector<SortedItem> sorted0;     // N_1: the lines, longest first (coordinate 0)
     std::vector<int32_t> line_order;     // N_1: lines ordered by length inside every chunk of kLineChunk
+    std::vector<SortedItem> eval_line;   // N_1: {padded coefficient offset, line length}
+    std::vector<EvalBlock> eval_block;   // blocks of lines staged together by the eval kernel
+    int64_t eval_padded = 0;             // size of the padded coefficient layout (doubles)
     std::vector<uint8_t> line_alpha;     // N_1 * (m-1): (a_1..a_{m-1}) of every line, for eval (n <= 255)
     // returns false (and sets the error) if A is not a colex-ordered downward-closed set
     bool build(const int64_t *A, int64_t N, int m, int n);

@@ -42,6 +42,7 @@ def lib():
         build()
         L = C.CDLL(_LIB_PATH)
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_lp_set.restype = C.c_int64
         L.orc_lp_set.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64]
         L.orc_lp_tube.restype = C.c_int64
@@ -57,6 +58,13 @@ def lib():
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def use_all_cores() -> int:
+    """Use every host core (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(n)
+    return num_threads()
 
 
 def lp_set(m: int, n: int, p: float) -> np.ndarray:
