@@ -105,7 +105,8 @@ enum {
                                    longest first: {first ent entry | line offset, lane | length << 8} */
     LPFNT_TAB_GROUPS = 15,      /* 2 * #groups int32: runs of <= 8 consecutive lanes of a fibre, tallest first:
                                    {first ent entry, lane0 | height << 8 | lanes << 16}               */
-    LPFNT_TAB_LINE_ORDER = 16   /* N_1 int32: lines ordered by length inside every chunk of 128 lines  */
+    LPFNT_TAB_LINE_ORDER = 16,  /* N_1 int32: lines ordered by length inside every chunk of 128 lines  */
+    LPFNT_TAB_GROUP_T = 17      /* 8 * #groups uint8: height of every lane of every lane group         */
 };
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);

@@ -124,9 +124,9 @@ def pinned_free(arr: np.ndarray):
 
 
 (TAB_LINE_OFF, TAB_FIB_PTR, TAB_FIB_ENT, TAB_THR_START, TAB_THR_FIB, TAB_LINE_ALPHA, TAB_LEVEL_SIZE,
- TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0, TAB_TILE_ROWPOS, TAB_TILE_ELEMROW, TAB_TILE_ELEM, TAB_TILE_NELEM, TAB_SORTED, TAB_GROUPS, TAB_LINE_ORDER) = range(17)
+ TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0, TAB_TILE_ROWPOS, TAB_TILE_ELEMROW, TAB_TILE_ELEM, TAB_TILE_NELEM, TAB_SORTED, TAB_GROUPS, TAB_LINE_ORDER, TAB_GROUP_T) = range(18)
 _TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_TILE_ITEMS: np.uint32, TAB_TILE_ROWS0: np.uint32,
-              TAB_TILE_ROWPOS: np.uint16, TAB_TILE_ELEMROW: np.uint8}
+              TAB_TILE_ROWPOS: np.uint16, TAB_TILE_ELEMROW: np.uint8, TAB_GROUP_T: np.uint8}
 
 
 class IndexTables:

@@ -33,6 +33,7 @@ struct DeviceDim {
     uint32_t *items = nullptr, *rows0 = nullptr;
     int4 *tile_rec = nullptr;
     int2 *sorted = nullptr, *groups = nullptr;
+    uint8_t *group_t = nullptr;
     uint16_t *ent_off16 = nullptr;           // line offsets in fibre order as uint16 (whole-function kernel, N < 65536)
     int32_t num_sorted = 0, num_groups = 0;
     int2 *tile_elem = nullptr;
@@ -80,6 +81,7 @@ struct lpfnt_plan {
     int debug_skip = 0;
     int use_whole = 0;                       // m <= 3: whole function in shared memory, one pass per transform (selectable;
                                              // measured on par with the per-coordinate kernels at d=3 n=30, slower for tiny N)
+    int use_two_lanes = 0;                   // two adjacent lanes per thread in the lane-group kernel
     int use_groups = 1;                      // height-ordered lane groups in the per-coordinate fibre kernel
     int use_sorted = 0;                      // globally length-sorted per-coordinate kernels (no shared memory)
     int use_pipe = 0;                        // persistent cp.async-pipelined variant of the row-tile kernels
@@ -233,7 +235,7 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
             if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
             const DeviceDim &d = p->dd[h];
             if (p->use_groups && d.groups) {
-                GroupSweepArgs ga{in, out, d.groups, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups};
+                GroupSweepArgs ga{in, out, d.groups, d.group_t, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups, p->use_two_lanes};
                 switch (cap) {
                     case 8: e = launch_group_sweep<8>(mode, spec.fma, ga, tri.data(), nb, s); break;
                     case 16: e = launch_group_sweep<16>(mode, spec.fma, ga, tri.data(), nb, s); break;
@@ -330,7 +332,7 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     a.perm_out = scatter ? p->d_perm : nullptr;
     a.n_elem = int(p->N); a.n_lines = int(p->N1); a.m = p->m;
     const size_t smem = whole_smem_bytes(int(p->N), int(p->N1));
-    const int threads = spec.fma ? 256 : 512;
+    const int threads = spec.fma ? 256 : 384;
     int occ = int(std::min<size_t>((size_t(227) * 1024) / (smem + 1024), size_t(2048 / threads)));
     occ = std::max(1, std::min(occ, spec.fma ? 2 : 1 + (smem < 100 * 1024)));
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
@@ -566,6 +568,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if (!D.groups.empty()) {
             d.num_groups = int32_t(D.groups.size());
             if ((rc = upload(&d.groups, reinterpret_cast<const int2 *>(D.groups.data()), D.groups.size(), p))) return fail(rc);
+            if ((rc = upload(&d.group_t, D.group_t.data(), D.group_t.size(), p))) return fail(rc);
         }
         if (!D.tile_fib.empty()) {
             d.num_tiles = int32_t(D.tile_fib.size()) - 1;
@@ -630,7 +633,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
-        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
+        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].group_t); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
     }
     for (int s = 0; s < 6; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -653,6 +656,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_two_lanes") == 0) { p->use_two_lanes = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_sorted") == 0) { p->use_sorted = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "debug_skip") == 0) { p->debug_skip = value ? 1 : 0; return LPFNT_OK; }

@@ -381,6 +381,16 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
             }
         }
         std::stable_sort(D.groups.begin(), D.groups.end(), [](const SortedItem &a, const SortedItem &b) { return ((a.y >> 8) & 0xff) > ((b.y >> 8) & 0xff); });
+        // height of every lane of every group (8 bytes per group, 0 for absent lanes)
+        D.group_t.assign(D.groups.size() * kGroupLanes, 0);
+        for (size_t g = 0; g < D.groups.size(); ++g) {
+            const int32_t p0 = D.groups[g].x, l0 = D.groups[g].y & 0xff, nl = (D.groups[g].y >> 8) & 0xff, lanes = (D.groups[g].y >> 16) & 0xff;
+            for (int32_t sub = 0; sub < lanes; ++sub) {
+                int32_t t = 0;
+                while (t < nl && D.ent[p0 + t].len > l0 + sub) ++t;
+                D.group_t[g * kGroupLanes + sub] = static_cast<uint8_t>(t);
+            }
+        }
     }
     // lines ordered by length inside every chunk of kLineChunk consecutive lines (k_sweep_lines)
     line_order.resize(N1);
@@ -464,6 +474,7 @@ bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t
     if (what == LPFNT_TAB_THR_FIB) return set(D.thr_fib.data(), 4, D.thr_fib.size(), int64_t(D.thr_fib.size()));
     if (what == LPFNT_TAB_SORTED) return set(D.sorted.data(), 8, D.sorted.size(), int64_t(2 * D.sorted.size()));
     if (what == LPFNT_TAB_GROUPS) return set(D.groups.data(), 8, D.groups.size(), int64_t(2 * D.groups.size()));
+    if (what == LPFNT_TAB_GROUP_T) return set(D.group_t.data(), 1, D.group_t.size(), int64_t(D.group_t.size()));
     if (what == LPFNT_TAB_TILE_FIB) return set(D.tile_fib.data(), 4, D.tile_fib.size(), int64_t(D.tile_fib.size()));
     if (what == LPFNT_TAB_TILE_ITEMS) return set(D.items.data(), 4, D.items.size(), int64_t(D.items.size()));
     if (what == LPFNT_TAB_TILE_ROWS0) return set(D.rows0.data(), 4, D.rows0.size(), int64_t(D.rows0.size()));

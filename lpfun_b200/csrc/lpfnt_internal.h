@@ -47,6 +47,7 @@ struct DimTable {
     // row tiles (see HostIndex::build): tile -> fibre range; per tile the element-fibres and rows
     // sorted by length.  item = row_rel | lane << 16 | t << 24 ; row0 = row_rel | len << 24
     std::vector<SortedItem> sorted;      // num_threads: element-fibres, longest first
+    std::vector<uint8_t> group_t;        // 8 per group: height of every lane of the run
     std::vector<SortedItem> groups;      // lane runs {first ent entry, lane0 | t << 8 | lanes << 16}, tallest first
     std::vector<int32_t> tile_fib;       // num_tiles + 1
     std::vector<uint32_t> items;         // num_threads (indexed like the threads: thr_start[f0] + j)

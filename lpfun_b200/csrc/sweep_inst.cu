@@ -97,6 +97,11 @@ cudaError_t launch_sorted_sweep<T>(int mode, bool fma, bool dim0, const SortedSw
 namespace {
 template <int MODE, bool FMA>
 cudaError_t group_launch(const GroupSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
+    if (a.two_lanes && (MODE == kLowerMatvec || MODE == kUpperMatvec)) {
+        dim3 grid((4 * int64_t(a.num_groups) + kSweepThreads - 1) / kSweepThreads, batch);
+        k_sweep_groups2<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
+        return cudaGetLastError();
+    }
     dim3 grid((8 * int64_t(a.num_groups) + kSweepThreads - 1) / kSweepThreads, batch);
     k_sweep_groups<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
@@ -138,8 +143,8 @@ cudaError_t launch_whole<T>(int mode, bool fma, const WholeArgs &a, const double
     std::memcpy(M.v, tri, sizeof(M.v));
     // exact arithmetic: one fibre per thread and many warps; FMA: two fibres per thread share the constants
     switch (mode) {
-        case kLowerMatvec: return fma ? whole_launch<kLowerMatvec, true, 2, 256>(a, M, grid, s) : whole_launch<kLowerMatvec, false, 1, 512>(a, M, grid, s);
-        case kLowerSolve: return whole_launch<kLowerSolve, false, 1, 512>(a, M, grid, s);
+        case kLowerMatvec: return fma ? whole_launch<kLowerMatvec, true, 2, 256>(a, M, grid, s) : whole_launch<kLowerMatvec, false, 1, 384>(a, M, grid, s);
+        case kLowerSolve: return whole_launch<kLowerSolve, false, 1, 384>(a, M, grid, s);
         default: return cudaErrorInvalidValue;
     }
 }

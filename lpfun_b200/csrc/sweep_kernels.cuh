@@ -44,21 +44,32 @@ template <int MAXT, int MODE, bool FMA>
 __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M) {
     if constexpr (MODE == kLowerMatvec) {
         // Outputs from the top down: out_k only reads x_j, j <= k, so it may overwrite x_k.
-        // Two rows are folded side by side (independent accumulators) to halve the dependent
-        // DADD/DFMA chain a lone warp sees; each row keeps its own ascending-j order.
-        static_assert(MAXT % 2 == 0, "rows are processed in pairs");
+        // FOUR rows are folded side by side (independent accumulators): the sweeps are latency
+        // bound (ncu: "wait" is the top stall at 20 warps/SM), and four chains per thread hide the
+        // 8.4-cycle DADD/DFMA latency twice as well as two; each row keeps its own ascending-j order.
+        // Rows of a block that lie beyond the fibre (k >= t) are computed on zeros and never stored.
+        static_assert(MAXT % 4 == 0, "rows are processed in blocks of four");
 #pragma unroll
-        for (int k = MAXT - 1; k >= 1; k -= 2) {
-            if (k - 1 < t) {  // row k-1 is needed; row k rides along (never stored when k == t)
-                double a1 = 0.0, a0 = 0.0;
+        for (int k = MAXT - 1; k >= 3; k -= 4) {
+            if (k - 3 < t) {
+                double a3 = 0.0, a2 = 0.0, a1 = 0.0, a0 = 0.0;
 #pragma unroll
-                for (int j = 0; j < k; ++j) {
-                    a1 = mac<FMA>(a1, M.v[k * (k + 1) / 2 + j], x[j]);
-                    a0 = mac<FMA>(a0, M.v[(k - 1) * k / 2 + j], x[j]);
+                for (int j = 0; j <= k - 3; ++j) {
+                    a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + j], x[j]);
+                    a2 = mac<FMA>(a2, M.v[(k - 1) * k / 2 + j], x[j]);
+                    a1 = mac<FMA>(a1, M.v[(k - 2) * (k - 1) / 2 + j], x[j]);
+                    a0 = mac<FMA>(a0, M.v[(k - 3) * (k - 2) / 2 + j], x[j]);
                 }
-                a1 = mac<FMA>(a1, M.v[k * (k + 1) / 2 + k], x[k]);
-                x[k] = a1;
-                x[k - 1] = a0;
+                a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + k - 2], x[k - 2]);
+                a2 = mac<FMA>(a2, M.v[(k - 1) * k / 2 + k - 2], x[k - 2]);
+                a1 = mac<FMA>(a1, M.v[(k - 2) * (k - 1) / 2 + k - 2], x[k - 2]);
+                a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + k - 1], x[k - 1]);
+                a2 = mac<FMA>(a2, M.v[(k - 1) * k / 2 + k - 1], x[k - 1]);
+                a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + k], x[k]);
+                x[k] = a3;
+                x[k - 1] = a2;
+                x[k - 2] = a1;
+                x[k - 3] = a0;
             }
         }
     } else if constexpr (MODE == kUpperMatvec) {
@@ -620,40 +631,45 @@ struct GroupSweepArgs {
     const double *in;
     double *out;
     const int2 *groups;       // {first ent entry, lane0 | height << 8 | lanes << 16}
+    const uint8_t *group_t;   // 8 per group: height of every lane
     const int2 *ent;
     const int32_t *perm_out;
     int64_t stride;
     int32_t num_groups;
+    int32_t two_lanes;        // 1: k_sweep_groups2 (two adjacent lanes per thread)
 };
 
 template <int MAXT, int MODE, bool FMA, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+__global__ void __launch_bounds__(THREADS, 6) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     const int j = blockIdx.x * THREADS + threadIdx.x;
     const int g = j >> 3, sub = j & 7;
-    if (g >= a.num_groups) return;
-    const int2 gr = __ldg(a.groups + g);
-    if (sub >= ((gr.y >> 16) & 0xff)) return;
+    const bool live = g < a.num_groups;  // whole warps stay alive for the shuffles below
+    const int2 gr = live ? __ldg(a.groups + g) : make_int2(0, 0);
+    const int p0 = gr.x, lane = (gr.y & 0xff) + sub, nl = (gr.y >> 8) & 0xff;
+    const int t = live ? int(__ldg(a.group_t + j)) : 0;  // height of this lane (0: lane absent)
     const double *in = a.in + int64_t(blockIdx.y) * a.stride;
     double *out = a.out + int64_t(blockIdx.y) * a.stride;
-    const int p0 = gr.x, lane = (gr.y & 0xff) + sub, nl = (gr.y >> 8) & 0xff;  // nl = height of the run's first lane
+    // The <= MAXT row offsets of the run are fetched ONCE, four per thread (rows sub, sub+8, ...),
+    // and handed around the 8 threads of the run with shuffles: one global latency ahead of the
+    // data loads instead of a dependent descriptor load per row, and nothing to re-load for the stores
+    // (ncu: descriptor look-ups and their dependent compares were 2/3 of the issued instructions).
+    constexpr int NR = MAXT / 8;
+    int offs[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) offs[i] = (sub + 8 * i < nl) ? __ldg(a.ent + p0 + sub + 8 * i).x : 0;
+    const int src_base = (threadIdx.x & 31) & ~7;
     double x[MAXT];
-    int t = 0;
 #pragma unroll
     for (int k = 0; k < MAXT; ++k) {
-        x[k] = 0.0;
-        if (k < nl) {
-            const int2 en = __ldg(a.ent + p0 + k);
-            if (en.y > lane) {
-                x[k] = in[en.x + lane];
-                t = k + 1;
-            }
-        }
+        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
+        x[k] = (k < t) ? in[off + lane] : 0.0;
     }
     apply_fibre<MAXT, MODE, FMA>(x, t, M);
 #pragma unroll
     for (int k = 0; k < MAXT; ++k) {
+        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
         if (k < t) {
-            const int e = __ldg(a.ent + p0 + k).x + lane;
+            const int e = off + lane;
             out[a.perm_out ? a.perm_out[e] : e] = x[k];
         }
     }
@@ -788,6 +804,58 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole(const WholeArgs a, const _
         } else {
 #pragma unroll 4
             for (int i = tid; i < N; i += THREADS) out[i] = buf[i];
+        }
+    }
+}
+
+// Two ADJACENT lanes per thread (same fibre, lanes 2s and 2s+1 of a height-ordered lane group):
+// the row descriptor, the address arithmetic and the matrix constants are shared by two element-
+// fibres, which halves the non-FP64 instructions per term (ncu: 2.5-3.8 issued instructions per
+// term besides the DMUL/DADD in the one-lane kernels).  Heights never increase along the lanes,
+// so the first lane's height bounds both (apply_fibre2).
+template <int MAXT, int MODE, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 3) k_sweep_groups2(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    const int j = blockIdx.x * THREADS + threadIdx.x;
+    const int g = j >> 2, sub = (j & 3) * 2;
+    if (g >= a.num_groups) return;
+    const int2 gr = __ldg(a.groups + g);
+    const int lanes = (gr.y >> 16) & 0xff;
+    if (sub >= lanes) return;
+    const bool two = sub + 1 < lanes;
+    const double *in = a.in + int64_t(blockIdx.y) * a.stride;
+    double *out = a.out + int64_t(blockIdx.y) * a.stride;
+    const int p0 = gr.x, lane = (gr.y & 0xff) + sub, nl = (gr.y >> 8) & 0xff;
+    double x[MAXT], y[MAXT];
+    int t0 = 0, t1 = 0;
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {
+        x[k] = 0.0;
+        y[k] = 0.0;
+        if (k < nl) {
+            const int2 en = __ldg(a.ent + p0 + k);
+            if (en.y > lane) {
+                const double *src = in + en.x + lane;
+                x[k] = src[0];
+                t0 = k + 1;
+                if (two && en.y > lane + 1) {
+                    y[k] = src[1];
+                    t1 = k + 1;
+                }
+            }
+        }
+    }
+    apply_fibre2<MAXT, MODE, FMA>(x, y, t0, M);
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {
+        if (k < t0) {
+            const int e = __ldg(a.ent + p0 + k).x + lane;
+            if (a.perm_out) {
+                out[a.perm_out[e]] = x[k];
+                if (k < t1) out[a.perm_out[e + 1]] = y[k];
+            } else {
+                out[e] = x[k];
+                if (k < t1) out[e + 1] = y[k];
+            }
         }
     }
 }
