@@ -39,6 +39,22 @@ __device__ __forceinline__ double mac(double acc, double a, double b) {
     else return __dadd_rn(acc, __dmul_rn(a, b));
 }
 
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+
 // Apply the triangular operator to a register-resident fibre of length t, in place.
 template <int MAXT, int MODE, bool FMA>
 __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M) {
@@ -184,11 +200,22 @@ __global__ void __launch_bounds__(THREADS) k_sweep_lines(const LineSweepArgs a, 
     const double *in = a.in + int64_t(blockIdx.y) * a.stride;
     double *out = a.out + int64_t(blockIdx.y) * a.stride;
 
+    // every element of the chunk is requested before anything waits (cp.async, no register staging)
     if (a.perm_in) {
-        for (int i = threadIdx.x; i < cnt; i += THREADS) buf[i] = in[a.perm_in[e0 + i]];
+        for (int ib = threadIdx.x; ib < cnt; ib += 8 * THREADS) {
+            int src[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) src[u] = (ib + u * THREADS < cnt) ? __ldg(a.perm_in + e0 + ib + u * THREADS) : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (ib + u * THREADS < cnt) cp_async8(buf + ib + u * THREADS, in + src[u]);
+        }
     } else {
-        for (int i = threadIdx.x; i < cnt; i += THREADS) buf[i] = in[e0 + i];
+#pragma unroll 4
+        for (int i = threadIdx.x; i < cnt; i += THREADS) cp_async8(buf + i, in + e0 + i);
     }
+    cp_async_commit();
+    cp_async_wait_all();
     __syncthreads();
     if (l0 + int(threadIdx.x) < l1) {
         const int l = a.line_order[l0 + threadIdx.x];  // the threadIdx.x-th longest line of the chunk
@@ -204,8 +231,10 @@ __global__ void __launch_bounds__(THREADS) k_sweep_lines(const LineSweepArgs a, 
     }
     __syncthreads();
     if (a.perm_out) {
-        for (int i = threadIdx.x; i < cnt; i += THREADS) out[a.perm_out[e0 + i]] = buf[i];
+#pragma unroll 4
+        for (int i = threadIdx.x; i < cnt; i += THREADS) out[__ldg(a.perm_out + e0 + i)] = buf[i];
     } else {
+#pragma unroll 4
         for (int i = threadIdx.x; i < cnt; i += THREADS) out[e0 + i] = buf[i];
     }
 }
@@ -258,22 +287,6 @@ __global__ void __launch_bounds__(THREADS) k_sweep_fibres(const FibreSweepArgs a
         }
     }
 }
-
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 
 struct TileSweepArgs {
     const double *in;
