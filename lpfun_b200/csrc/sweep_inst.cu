@@ -149,6 +149,28 @@ cudaError_t launch_whole<T>(int mode, bool fma, const WholeArgs &a, const double
     }
 }
 
+namespace {
+template <int MODE, bool FMA>
+cudaError_t plane_launch(const PlaneSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
+    dim3 grid((a.num_planes + 3) / 4, batch);
+    k_sweep_planes<T, MODE, FMA><<<grid, 128, 0, s>>>(a, M);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <>
+cudaError_t launch_plane_sweep<T>(int mode, bool fma, const PlaneSweepArgs &a, const double *tri, int batch, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? plane_launch<kLowerMatvec, true>(a, M, batch, s) : plane_launch<kLowerMatvec, false>(a, M, batch, s);
+        case kUpperMatvec: return fma ? plane_launch<kUpperMatvec, true>(a, M, batch, s) : plane_launch<kUpperMatvec, false>(a, M, batch, s);
+        case kLowerSolve: return plane_launch<kLowerSolve, false>(a, M, batch, s);
+        case kUpperSolve: return plane_launch<kUpperSolve, false>(a, M, batch, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <>
 cudaError_t launch_tile_sweep<T>(int mode, bool fma, bool dim0, const TileSweepArgs &a, const double *tri, int max_line, int num_tiles, int batch, cudaStream_t s) {
     PackedTri<T> M;

@@ -874,6 +874,105 @@ __global__ void __launch_bounds__(THREADS, 3) k_sweep_groups2(const GroupSweepAr
 }
 
 // ---------------------------------------------------------------------------------------
+// Coordinates 0 AND 1 in one pass, one WARP per plane (fixed a_2.., all a_0, a_1).
+// A plane is <= n+1 contiguous lines of <= n+1 elements.  The warp copies the lines into its
+// private slab of shared memory (row pitch MAXT+1, coalesced loads, descriptors handed around
+// with shuffles), sweeps coordinate 0 with lane <-> line, re-reads the slab transposed
+// (lane <-> a_0) for coordinate 1 and stores straight from registers (lanes = consecutive a_0:
+// coalesced).  No CTA barrier (only __syncwarp), four shared-memory trips per element, one pass
+// over memory fewer than the per-coordinate kernels.  The lanes of a warp run triangles of
+// different size here (heights fall along a plane), i.e. some FP64 lanes idle -- the sweeps
+// are latency / pass-count bound, not FP64 bound, so the saved pass wins.
+// Grid: (ceil(planes / 4), batch), 128 threads.
+// ---------------------------------------------------------------------------------------
+struct PlaneSweepArgs {
+    const double *in;
+    double *out;
+    const int32_t *line_off;   // N_1 + 1
+    const int32_t *plane_line; // planes + 1: first line of every plane (CSR)
+    const int32_t *perm_in;
+    const int32_t *perm_out;
+    int64_t stride;
+    int32_t num_planes;
+};
+
+template <int MAXT, int MODE, bool FMA>
+__global__ void __launch_bounds__(128, 6) k_sweep_planes(const PlaneSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    constexpr int PAD = MAXT + 1;
+    __shared__ double slab[4][MAXT * PAD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int plane = blockIdx.x * 4 + warp;
+    if (plane >= a.num_planes) return;
+    double *buf = slab[warp];
+    const double *in = a.in + int64_t(blockIdx.y) * a.stride;
+    double *out = a.out + int64_t(blockIdx.y) * a.stride;
+    const int l0 = __ldg(a.plane_line + plane), nl = __ldg(a.plane_line + plane + 1) - l0;
+    // lane r owns the descriptor of row r
+    int my_off = 0, my_len = 0;
+    if (lane < nl) {
+        my_off = __ldg(a.line_off + l0 + lane);
+        my_len = __ldg(a.line_off + l0 + lane + 1) - my_off;
+    }
+    // copy in: row r by all lanes (lane = a_0)
+    // (cp.async: every row of the plane is in flight at once; with the colex gather the permutation
+    // entries are fetched eight rows at a time first)
+    if (a.perm_in) {
+        for (int rb = 0; rb < nl; rb += 8) {
+            int src[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int off = __shfl_sync(0xffffffffu, my_off, (rb + u) & 31);
+                const int len = __shfl_sync(0xffffffffu, my_len, (rb + u) & 31);
+                src[u] = (rb + u < nl && lane < len) ? __ldg(a.perm_in + off + lane) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (src[u] >= 0) cp_async8(buf + (rb + u) * PAD + lane, in + src[u]);
+        }
+    } else {
+#pragma unroll 4
+        for (int r = 0; r < nl; ++r) {
+            const int off = __shfl_sync(0xffffffffu, my_off, r);
+            const int len = __shfl_sync(0xffffffffu, my_len, r);
+            if (lane < len) cp_async8(buf + r * PAD + lane, in + off + lane);
+        }
+    }
+    cp_async_commit();
+    // height of column a_0 = lane: rows whose length exceeds it (lengths never increase along a_1)
+    int t1 = 0;
+#pragma unroll 4
+    for (int r = 0; r < nl; ++r) t1 += (__shfl_sync(0xffffffffu, my_len, r) > lane) ? 1 : 0;
+    cp_async_wait_all();
+    __syncwarp();
+    {   // coordinate 0: lane <-> line
+        const int t = my_len;
+        double *row = buf + lane * PAD;
+        double x[MAXT];
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? row[k] : 0.0;
+        apply_fibre<MAXT, MODE, FMA>(x, t, M);
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k)
+            if (k < t) row[k] = x[k];
+    }
+    __syncwarp();
+    {   // coordinate 1: lane <-> a_0, element k = row k
+        double x[MAXT];
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) x[k] = (k < t1) ? buf[k * PAD + lane] : 0.0;
+        apply_fibre<MAXT, MODE, FMA>(x, t1, M);
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) {
+            const int off = __shfl_sync(0xffffffffu, my_off, k);
+            if (k < t1) {
+                const int e = off + lane;
+                out[a.perm_out ? a.perm_out[e] : e] = x[k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Generic fallback for fibres longer than the register kernels support (n + 1 > 32): same
 // thread <-> element-fibre mapping, matrix read from global memory in the REFERENCE packing,
 // fibre re-read from global memory (O(t^2) loads, L1/L2 resident).  `in` may equal `out`

@@ -37,6 +37,9 @@ inline size_t whole_smem_bytes(int n_elem, int n_lines) {
 template <int MAXT>
 cudaError_t launch_whole(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s);
 
+template <int MAXT>
+cudaError_t launch_plane_sweep(int mode, bool fma, const PlaneSweepArgs &a, const double *tri, int batch, cudaStream_t s);
+
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s);
 

@@ -306,6 +306,8 @@ def test_c5_dx_eval_vs_oracle(T):
     {"use_whole": 0, "use_sorted": 1},
     {"use_whole": 0, "use_groups": 0},
     {"use_whole": 1},
+    {"use_whole": 0, "use_planes": 1},
+    {"use_whole": 0, "use_two_lanes": 1},
 ])
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d6n4", "d2n7_inf", "d3n12_solve", "c4_d3n30"])
 def test_alternative_kernel_families(T, name, opts):
