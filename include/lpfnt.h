@@ -132,6 +132,12 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
                       const double *nodes, const double *Vx_lt, const double *inv_Vx_lt,
                       const double *const *Dx_ut, const double *const *DxT_lt, int device,
                       lpfnt_plan **plan);
+/* Bases whose Vandermonde matrix V is not triangular (basis="chebyshev"): V = L U without pivoting
+ * (get_lu, src/lpfun/utils.py:315-328).  Pass L as Vx_lt / inv(L) as inv_Vx_lt to lpfnt_plan_create and the
+ * packed UPPER factors here (transform.py:292-302).  fnt then runs the lower sweep with inv(L) followed by the
+ * upper sweep with inv(U) (transform.py:491-519), ifnt the upper sweep with U followed by the lower sweep
+ * with L (:596-624).  chebyshev_eval != 0 makes eval use the T_k recurrence (chebyshev2point, utils.py:165). */
+int lpfnt_plan_set_upper_factors(lpfnt_plan *plan, const double *Vx_ut, const double *inv_Vx_ut, int chebyshev_eval);
 int lpfnt_plan_destroy(lpfnt_plan *plan);
 /* bytes of device memory held by the plan (tables + workspaces) */
 int64_t lpfnt_plan_device_bytes(const lpfnt_plan *plan);

@@ -73,6 +73,10 @@ struct lpfnt_plan {
     std::vector<int64_t> hA;      // kept only when the generic eval may need it
     // host copies of the 1-D operators (reference packing)
     std::vector<double> nodes, Vx_lt, inv_Vx_lt, Dx_ut[3], DxT_lt[3];
+    // LU-factorised (non-triangular) V, e.g. the Chebyshev basis: upper factors; chebyshev_eval selects the
+    // T_k basis in eval (transform.py:292-302, utils.py:165-195)
+    std::vector<double> Vx_ut, inv_Vx_ut;
+    int chebyshev_eval = 0;
     // workspaces (grown on demand): two lanes x {staged input, staged output, permutation scratch}
     double *ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -174,7 +178,8 @@ int sweep_mode(const SweepSpec &s) {
 int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const double *src, double *dst, int64_t batch,
                bool gather, bool scatter, cudaStream_t s) {
     const int n1 = p->n + 1;
-    const int mode = sweep_mode(spec);
+    int mode = sweep_mode(spec);
+    if (mode == kUpperSolve && h >= 1) mode = kUpperSolveDesc;  // the reference's fold order there (atoms.py:391-402)
     const int len = (h == 0) ? p->max_line : std::max(p->dd[h].max_lines, fuse0 ? p->max_line : 0);
     const bool planes = fuse0 && h == 1 && p->use_planes && p->num_planes > 0;
     const bool tiles = !planes && h >= 1 && p->use_tiles && !p->use_sorted && p->dd[h].num_tiles > 0;
@@ -386,6 +391,10 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     gather = gather && p->has_perm;
     scatter = scatter && p->has_perm;
     if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
+    if (spec.solve && spec.kind == LPFNT_UPPER && (p->use_tiles || p->use_sorted || p->use_planes || p->use_pipe)) {
+        set_error("the upper triangular solve only runs on the default line/group kernels");
+        return LPFNT_EUNSUPPORTED;
+    }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
     if (whole_ok(p, spec, dims)) {
         // in-place is safe: a function is read completely into shared memory before it is written
@@ -459,12 +468,25 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
 }
 
 // Host-pointer front end: stage through ws[0]/ws[1] in chunks of functions.
-int run_any(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
+// Sequence of sweeps (one spec = one triangular operator applied along `dims`); gather rides on the first,
+// scatter on the last.
+int run_specs(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vector<int> &dims, const double *in, double *out,
+              int64_t batch, bool gather, bool scatter, cudaStream_t s, int mid_slot) {
+    const int ns = int(specs.size());
+    for (int i = 0; i < ns; ++i) {
+        int rc = run_device(p, specs[i], dims, i == 0 ? in : out, out, batch, gather && i == 0, scatter && i == ns - 1, s, mid_slot);
+        if (rc) return rc;
+    }
+    return LPFNT_OK;
+}
+
+int run_any(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vector<int> &dims, const double *in, double *out,
             int64_t batch, bool gather, bool scatter, int on_device, void *stream) {
     if (!p || !in || !out || batch < 1) { set_error("null pointer or empty batch"); return LPFNT_EINVAL; }
-    if (!spec.packed) { set_error("the plan was created without the matrix this operation needs"); return LPFNT_EINVAL; }
+    for (const SweepSpec &sp : specs)
+        if (!sp.packed) { set_error("the plan was created without the matrix this operation needs"); return LPFNT_EINVAL; }
     CK(cudaSetDevice(p->device));
-    if (on_device) return run_device(p, spec, dims, in, out, batch, gather, scatter, static_cast<cudaStream_t>(stream));
+    if (on_device) return run_specs(p, specs, dims, in, out, batch, gather, scatter, static_cast<cudaStream_t>(stream), 2);
     // Host pointers: cut the batch into chunks and run them on two lanes (streams) with their own staging
     // buffers, so that the H2D copy of chunk i+1 overlaps the sweeps and the D2H copy of chunk i
     // (PCIe is full duplex; the copies dominate this path by an order of magnitude).
@@ -484,13 +506,18 @@ int run_any(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, 
         const int l = (lanes == 2) ? (i & 1) : 0;
         cudaStream_t s = l ? p->stream2 : p->stream;
         CK(cudaMemcpyAsync(p->ws[3 * l], in + b0 * p->N, size_t(nb) * fbytes, cudaMemcpyHostToDevice, s));
-        int rc = run_device(p, spec, dims, p->ws[3 * l], p->ws[3 * l + 1], nb, gather, scatter, s, 3 * l + 2);
+        int rc = run_specs(p, specs, dims, p->ws[3 * l], p->ws[3 * l + 1], nb, gather, scatter, s, 3 * l + 2);
         if (rc) return rc;
         CK(cudaMemcpyAsync(out + b0 * p->N, p->ws[3 * l + 1], size_t(nb) * fbytes, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(p->stream));
     if (lanes == 2) CK(cudaStreamSynchronize(p->stream2));
     return LPFNT_OK;
+}
+
+int run_any(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
+            int64_t batch, bool gather, bool scatter, int on_device, void *stream) {
+    return run_any(p, std::vector<SweepSpec>{spec}, dims, in, out, batch, gather, scatter, on_device, stream);
 }
 
 std::vector<int> all_dims(int m) {
@@ -641,7 +668,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
     if (!hx.line_alpha.empty())
         if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
     // the generic eval needs A on the device; keep a host copy when that path can be reached
-    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255 || N * m <= (int64_t(1) << 23)) p->hA.assign(A, A + N * m);
+    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255 || N * m <= (int64_t(1) << 26)) p->hA.assign(A, A + N * m);
     if (nodes && (rc = upload(&p->d_nodes, nodes, size_t(n + 1), p))) return fail(rc);
     {
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_mat), sizeof(double) * ts);
@@ -748,8 +775,28 @@ int lpfnt_dtransform(lpfnt_plan *p, const double *packed, int kind, int arith, i
     return run_any(p, spec, std::vector<int>{i}, in, out, batch, false, false, on_device, stream);
 }
 
+int lpfnt_plan_set_upper_factors(lpfnt_plan *p, const double *Vx_ut, const double *inv_Vx_ut, int chebyshev_eval) {
+    if (!p || !Vx_ut) { set_error("set_upper_factors: need the packed upper factor of V"); return LPFNT_EINVAL; }
+    const int ts = tri_size(p->n + 1);
+    p->Vx_ut.assign(Vx_ut, Vx_ut + ts);
+    if (inv_Vx_ut) p->inv_Vx_ut.assign(inv_Vx_ut, inv_Vx_ut + ts);
+    else p->inv_Vx_ut.clear();
+    p->chebyshev_eval = chebyshev_eval ? 1 : 0;
+    return LPFNT_OK;
+}
+
 int lpfnt_fnt(lpfnt_plan *p, const double *in, double *out, int64_t batch, int on_device, void *stream) {
     if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (!p->Vx_ut.empty()) {
+        // V = L U (transform.py:491-519): lower mat-vec with inv(L), then upper mat-vec with inv(U)
+        if (p->inv_Vx_lt.empty() || p->inv_Vx_ut.empty()) {
+            // precomputation=False (transform.py:520-548): forward substitution with L, then backward with U
+            std::vector<SweepSpec> specs{{p->Vx_lt.empty() ? nullptr : p->Vx_lt.data(), LPFNT_LOWER, true, false}, {p->Vx_ut.data(), LPFNT_UPPER, true, false}};
+            return run_any(p, specs, all_dims(p->m), in, out, batch, true, false, on_device, stream);
+        }
+        std::vector<SweepSpec> specs{{p->inv_Vx_lt.data(), LPFNT_LOWER, false, false}, {p->inv_Vx_ut.data(), LPFNT_UPPER, false, false}};
+        return run_any(p, specs, all_dims(p->m), in, out, batch, true, false, on_device, stream);
+    }
     if (!p->inv_Vx_lt.empty()) {
         SweepSpec spec{p->inv_Vx_lt.data(), LPFNT_LOWER, false, false};
         return run_any(p, spec, all_dims(p->m), in, out, batch, true, false, on_device, stream);
@@ -760,7 +807,13 @@ int lpfnt_fnt(lpfnt_plan *p, const double *in, double *out, int64_t batch, int o
 
 int lpfnt_ifnt(lpfnt_plan *p, const double *in, double *out, int64_t batch, int arith, int on_device, void *stream) {
     if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
-    SweepSpec spec{p->Vx_lt.empty() ? nullptr : p->Vx_lt.data(), LPFNT_LOWER, false, arith == LPFNT_ARITH_FMA};
+    const bool fma = arith == LPFNT_ARITH_FMA;
+    if (!p->Vx_ut.empty()) {
+        // transform.py:596-624: upper mat-vec with U, then lower mat-vec with L
+        std::vector<SweepSpec> specs{{p->Vx_ut.data(), LPFNT_UPPER, false, fma}, {p->Vx_lt.empty() ? nullptr : p->Vx_lt.data(), LPFNT_LOWER, false, fma}};
+        return run_any(p, specs, all_dims(p->m), in, out, batch, false, true, on_device, stream);
+    }
+    SweepSpec spec{p->Vx_lt.empty() ? nullptr : p->Vx_lt.data(), LPFNT_LOWER, false, fma};
     return run_any(p, spec, all_dims(p->m), in, out, batch, false, true, on_device, stream);
 }
 
@@ -794,7 +847,7 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
     cudaStream_t s = on_device ? static_cast<cudaStream_t>(stream) : p->stream;
     const double *dc = coeffs, *dp = points;
     double *dv = values;
-    const bool fast = !p->force_generic && (p->n + 1 <= kMaxRegT) && p->m <= kEvalMaxM && p->n <= 255 && (p->m == 1 || p->d_line_alpha);
+    const bool fast = !p->chebyshev_eval && !p->force_generic && (p->n + 1 <= kMaxRegT) && p->m <= kEvalMaxM && p->n <= 255 && (p->m == 1 || p->d_line_alpha);
     const size_t cb = size_t(p->N) * sizeof(double), pb = size_t(P) * p->m * sizeof(double), vb = size_t(P) * sizeof(double);
     if (!on_device) {
         int rc = ensure_ws(p, 0, cb + pb);
@@ -846,7 +899,7 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
         if (rc) return rc;
         for (int64_t q0 = 0; q0 < P; q0 += step) {
             const int64_t np = std::min(step, P - q0);
-            EvalGenericArgs a{dc, dp + q0 * p->m, p->d_nodes, dv + q0, p->d_A, p->ws[2], np, p->N, p->m, p->n};
+            EvalGenericArgs a{dc, dp + q0 * p->m, p->d_nodes, dv + q0, p->d_A, p->ws[2], np, p->N, p->m, p->n, p->chebyshev_eval};
             cudaError_t e = launch_eval_generic(a, s);
             p->launches += 1;
             if (e != cudaSuccess) { set_error(std::string("eval launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }

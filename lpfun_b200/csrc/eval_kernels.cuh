@@ -292,6 +292,7 @@ struct EvalGenericArgs {
     double *scratch;  // num_points * m * (n+1) doubles
     int64_t num_points, N;
     int32_t m, n;
+    int32_t chebyshev;  // 1: T_k basis by the three-term recurrence (chebyshev2point, utils.py:165-195)
 };
 
 #ifdef LPFNT_EVAL_TU  // defined once, in eval_inst.cu
@@ -303,7 +304,13 @@ __global__ void __launch_bounds__(128) k_eval_generic(const EvalGenericArgs a) {
     for (int i = 0; i < m; ++i) {
         const double xi = a.points[p * m + i];
         basis[i * n1] = 1.0;
-        for (int q = 1; q < n1; ++q) basis[i * n1 + q] = __dmul_rn(basis[i * n1 + q - 1], __dsub_rn(xi, a.nodes[q - 1]));
+        if (a.chebyshev) {
+            if (n1 > 1) basis[i * n1 + 1] = xi;
+            for (int q = 1; q + 1 < n1; ++q)
+                basis[i * n1 + q + 1] = __dsub_rn(__dmul_rn(__dmul_rn(2.0, xi), basis[i * n1 + q]), basis[i * n1 + q - 1]);
+        } else {
+            for (int q = 1; q < n1; ++q) basis[i * n1 + q] = __dmul_rn(basis[i * n1 + q - 1], __dsub_rn(xi, a.nodes[q - 1]));
+        }
     }
     double value = 0.0;
     for (int64_t r = 0; r < a.N; ++r) {

@@ -117,6 +117,7 @@ cudaError_t launch_group_sweep<T>(int mode, bool fma, const GroupSweepArgs &a, c
         case kUpperMatvec: return fma ? group_launch<kUpperMatvec, true>(a, M, batch, s) : group_launch<kUpperMatvec, false>(a, M, batch, s);
         case kLowerSolve: return group_launch<kLowerSolve, false>(a, M, batch, s);
         case kUpperSolve: return group_launch<kUpperSolve, false>(a, M, batch, s);
+        case kUpperSolveDesc: return group_launch<kUpperSolveDesc, false>(a, M, batch, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -206,6 +207,7 @@ cudaError_t launch_fibre_sweep<T>(int mode, bool fma, const FibreSweepArgs &a, c
         case kUpperMatvec: return fma ? fibre_launch<kUpperMatvec, true>(a, M, batch, s) : fibre_launch<kUpperMatvec, false>(a, M, batch, s);
         case kLowerSolve: return fibre_launch<kLowerSolve, false>(a, M, batch, s);
         case kUpperSolve: return fibre_launch<kUpperSolve, false>(a, M, batch, s);
+        case kUpperSolveDesc: return fibre_launch<kUpperSolveDesc, false>(a, M, batch, s);
     }
     return cudaErrorInvalidValue;
 }

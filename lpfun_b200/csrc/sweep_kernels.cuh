@@ -22,7 +22,10 @@ enum SweepMode : int {
     kLowerMatvec = 0,  // out_k = sum_{j<=k} L[k,j] x_j                (fnt with inv V, ifnt, dxT)
     kUpperMatvec = 1,  // out_k = sum_{j>=k} U[k,j] x_j                (dx)
     kLowerSolve = 2,   // out_k = (x_k - sum_{j<k} L[k,j] out_j)/L[k,k] (fnt, precomputation=False)
-    kUpperSolve = 3    // out_k = (x_k - (U[k,k]*0 + sum_{j>k} U[k,j] out_j))/U[k,k]
+    kUpperSolve = 3,   // out_k = (x_k - (U[k,k]*0 + sum_{j>k} U[k,j] out_j))/U[k,k], j ascending (coordinate 0:
+                       // transform_ut_1d / the 1d stage of transform_ut_2d/3d/md, atoms.py:54-69, 372-385)
+    kUpperSolveDesc = 4  // same, j DEscending: coordinates >= 1 accumulate the leaders last-to-first
+                         // (atoms.py:391-402, 975-1003)
 };
 
 // Packed triangle with COMPILE-TIME offsets, independent of n:
@@ -107,6 +110,17 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < k; ++j) s = mac<false>(s, M.v[k * (k + 1) / 2 + j], x[j]);
+                x[k] = __ddiv_rn(__dsub_rn(x[k], s), M.v[k * (k + 1) / 2 + k]);
+            }
+        }
+    } else if constexpr (MODE == kUpperSolveDesc) {
+#pragma unroll
+        for (int k = MAXT - 1; k >= 0; --k) {
+            if (k < t) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = MAXT - 1; j > k; --j)
+                    if (j < t) s = mac<false>(s, M.v[j * (j + 1) / 2 + k], x[j]);
                 x[k] = __ddiv_rn(__dsub_rn(x[k], s), M.v[k * (k + 1) / 2 + k]);
             }
         }
@@ -1055,6 +1069,16 @@ __global__ void __launch_bounds__(128) k_sweep_generic(const GenericArgs a) {
                 s = mac_rt(s, row[q], out[a.perm_out ? a.perm_out[e] : e], 0);
             }
             wr(k, __ddiv_rn(__dsub_rn(rd(k), s), row[k]));
+        }
+    } else if (a.mode == kUpperSolveDesc) {
+        for (int k = t - 1; k >= 0; --k) {
+            const double *row = a.mat + int64_t(k) * n1 - int64_t(k) * (k - 1) / 2;
+            double s = 0.0;
+            for (int q = t - 1; q > k; --q) {
+                const int e = pos(q);
+                s = mac_rt(s, row[q - k], out[a.perm_out ? a.perm_out[e] : e], 0);
+            }
+            wr(k, __ddiv_rn(__dsub_rn(rd(k), s), row[0]));
         }
     } else {
         for (int k = t - 1; k >= 0; --k) {

@@ -72,10 +72,6 @@ class Transform:
         U.classify(self._m, self._n, self._p)
         if basis not in ("newton", "chebyshev"):
             raise ValueError("Invalid choice for basis.")
-        if basis == "chebyshev":
-            raise NotImplementedError(
-                "basis='chebyshev' (LU two-pass sweeps) is outside the accelerated hot path; see DESIGN.md 'next rows'."
-            )
 
         # --- index structure (transform.py:207-232) ---
         self._A = lpset.lp_set(self._m, self._n, self._p)
@@ -109,13 +105,27 @@ class Transform:
             self._grid = grid
 
         # --- 1-D operators, packed exactly like the reference (transform.py:268-336) ---
-        self._Vx = U.newton2lagrange(self._x)
-        self._Dx = U.newton2derivative(self._x)
+        if basis == "newton":
+            self._Vx = U.newton2lagrange(self._x)
+            self._Dx = U.newton2derivative(self._x)
+        else:
+            self._Vx = U.chebyshev2lagrange(self._x)
+            self._Dx = U.chebyshev2derivative(self._x)
         self._Dx2 = self._Dx @ self._Dx
         self._Dx3 = self._Dx @ self._Dx2
         self._cond_Vx = float(np.linalg.cond(self._Vx))
-        self._Vx_lt = U.pack_lower(self._Vx)
-        self._inv_Vx_lt = U.pack_lower(np.linalg.inv(self._Vx)) if precomputation else None
+        self._Vx_ut = self._inv_Vx_ut = None
+        if U.is_lower_triangular(self._Vx):
+            self._Vx_lt = U.pack_lower(self._Vx)
+            self._inv_Vx_lt = U.pack_lower(np.linalg.inv(self._Vx)) if precomputation else None
+        else:
+            # V = L U without pivoting (transform.py:292-302)
+            Lf, Uf = U.get_lu(self._Vx)
+            self._Vx_lt, self._Vx_ut = U.pack_lower(Lf), U.pack_upper(Uf)
+            self._inv_Vx_lt = U.pack_lower(np.linalg.inv(Lf)) if precomputation else None
+            self._inv_Vx_ut = U.pack_upper(np.linalg.inv(Uf)) if precomputation else None
+        if not U.is_lower_triangular(self._Dx.T):
+            raise NotImplementedError("differentiation matrices that are not upper triangular need the LU path (not implemented)")
         self._Dx_lt = [U.pack_upper(D) for D in (self._Dx, self._Dx2, self._Dx3)]  # reference name; upper packed
         self._DxT_lt = [U.pack_lower(D.T) for D in (self._Dx, self._Dx2, self._Dx3)]
         self._construction_ms = (time.time() - t0) * 1000
@@ -141,6 +151,8 @@ class Transform:
             self._Vx_lt.ctypes.data, nat.ptr(self._inv_Vx_lt), dptr, tptr, self._device, C.byref(plan),
         )
         nat.check(rc)
+        if self._Vx_ut is not None:
+            nat.check(L.lpfnt_plan_set_upper_factors(plan, self._Vx_ut.ctypes.data, nat.ptr(self._inv_Vx_ut), int(self._basis == "chebyshev")))
         return plan
 
     def close(self):
@@ -190,6 +202,10 @@ class Transform:
     @property
     def leja_order(self) -> np.ndarray:
         return self._leja_order
+
+    @property
+    def basis(self) -> str:
+        return self._basis
 
     @property
     def device(self) -> int:

@@ -9,7 +9,7 @@ bit-for-bit with outputs of the unmodified reference stored in tests/golden/
 26 Transforms incl. the five BASELINE configs).
 
 ``OracleTransform`` mirrors the reference ``Transform`` front-end
-(src/lpfun/transform.py:95-928) for the Newton basis on top of the C sweeps.
+(src/lpfun/transform.py:95-928) for both bases on top of the C sweeps.
 """
 from __future__ import annotations
 
@@ -51,6 +51,8 @@ def lib():
         L.orc_sweep_lower_matvec.argtypes = [_f64p, _f64p, _f64p, _i64p, C.c_int64, C.c_int, C.c_int, _i32p]
         L.orc_sweep_upper_matvec.argtypes = [_f64p, C.c_int, _f64p, _f64p, _i64p, C.c_int64, C.c_int, C.c_int, _i32p, C.c_int]
         L.orc_sweep_lower_solve.argtypes = [_f64p, _f64p, _f64p, _i64p, C.c_int64, C.c_int, C.c_int, _i32p]
+        L.orc_sweep_upper_solve.argtypes = [_f64p, C.c_int, _f64p, _f64p, _i64p, C.c_int64, C.c_int, C.c_int, _i32p]
+        L.orc_chebyshev2point.argtypes = [_f64p, _f64p, C.c_int64, _i64p, C.c_int64, C.c_int, C.c_int, _f64p]
         L.orc_newton2point.argtypes = [_f64p, _f64p, _f64p, C.c_int64, _i64p, C.c_int64, C.c_int, C.c_int, _f64p]
         _lib = L
     return _lib
@@ -129,6 +131,15 @@ class Sweeper:
             x = out
         return x
 
+    def upper_solve(self, Up, n1, x, dims=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        Up = np.ascontiguousarray(Up, dtype=np.float64)
+        for h in (range(self.m) if dims is None else dims):
+            out = np.zeros_like(x)
+            lib().orc_sweep_upper_solve(Up, int(n1), x, out, self.A, self.N, self.m, h, self.neighbors(h)[1])
+            x = out
+        return x
+
     def eval(self, c, nodes, pts, n):
         c = np.ascontiguousarray(c, dtype=np.float64)
         pts = np.ascontiguousarray(pts, dtype=np.float64)
@@ -137,16 +148,23 @@ class Sweeper:
         lib().orc_newton2point(c, nodes, pts, len(pts), self.A, self.N, self.m, int(n), out)
         return out
 
+    def eval_chebyshev(self, c, pts, n):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        out = np.empty(len(pts), dtype=np.float64)
+        lib().orc_chebyshev2point(c, pts, len(pts), self.A, self.N, self.m, int(n), out)
+        return out
+
 
 class OracleTransform:
-    """CPU mirror of the reference Transform (Newton basis).
+    """CPU mirror of the reference Transform (Newton and Chebyshev bases).
 
     Matrices are taken from the caller (golden fixtures) or built with the host
     numerics in lpfun_b200.utils, which are themselves pinned against the
     reference's matrices by tests/test_host_golden.py.
     """
 
-    def __init__(self, m, n, p=2.0, nodes="cheb2nd", precomputation=True, colex_order=True, mats=None):
+    def __init__(self, m, n, p=2.0, nodes="cheb2nd", precomputation=True, colex_order=True, mats=None, basis="newton"):
         from lpfun_b200 import utils as U  # host numerics only (no GPU code)
 
         self.m, self.n, self.p = int(m), int(n), float(p)
@@ -164,15 +182,22 @@ class OracleTransform:
             self.grid[self.P] = grid_int
         else:
             self.P, self.grid = None, grid_int
+        self.basis = basis
         if mats is None:
-            Vx = U.newton2lagrange(self.x)
-            Dx = U.newton2derivative(self.x)
+            cheb = basis == "chebyshev"
+            Vx = (U.chebyshev2lagrange if cheb else U.newton2lagrange)(self.x)
+            Dx = (U.chebyshev2derivative if cheb else U.newton2derivative)(self.x)
             Dx2 = Dx @ Dx
             Dx3 = Dx @ Dx2
-            mats = dict(Vx_lt=U.pack_lower(Vx),
-                        inv_Vx_lt=U.pack_lower(np.linalg.inv(Vx)) if precomputation else None,
-                        Dx_ut=[U.pack_upper(D) for D in (Dx, Dx2, Dx3)],
+            mats = dict(Dx_ut=[U.pack_upper(D) for D in (Dx, Dx2, Dx3)],
                         DxT_lt=[U.pack_lower(D.T) for D in (Dx, Dx2, Dx3)])
+            if U.is_lower_triangular(Vx):
+                mats.update(Vx_lt=U.pack_lower(Vx), inv_Vx_lt=U.pack_lower(np.linalg.inv(Vx)) if precomputation else None)
+            else:  # src/lpfun/transform.py:292-302
+                Lf, Uf = U.get_lu(Vx)
+                mats.update(Vx_lt=U.pack_lower(Lf), Vx_ut=U.pack_upper(Uf),
+                            inv_Vx_lt=U.pack_lower(np.linalg.inv(Lf)) if precomputation else None,
+                            inv_Vx_ut=U.pack_upper(np.linalg.inv(Uf)) if precomputation else None)
         self.mats = mats
         self.precomputation = precomputation
 
@@ -184,13 +209,21 @@ class OracleTransform:
         v = np.asarray(values, dtype=np.float64)
         if self.P is not None:
             v = v[self.P]
+        n1 = self.n + 1
+        if self.mats.get("Vx_ut") is not None:  # LU two-pass, transform.py:491-548
+            if self.precomputation:
+                return self.sw.upper_matvec(self.mats["inv_Vx_ut"], n1, self.sw.lower_matvec(self.mats["inv_Vx_lt"], v))
+            return self.sw.upper_solve(self.mats["Vx_ut"], n1, self.sw.lower_solve(self.mats["Vx_lt"], v))
         if self.precomputation:
             return self.sw.lower_matvec(self.mats["inv_Vx_lt"], v)
         return self.sw.lower_solve(self.mats["Vx_lt"], v)
 
     # src/lpfun/transform.py:553-632
     def ifnt(self, coeffs):
-        y = self.sw.lower_matvec(self.mats["Vx_lt"], np.asarray(coeffs, dtype=np.float64))
+        c = np.asarray(coeffs, dtype=np.float64)
+        if self.mats.get("Vx_ut") is not None:  # transform.py:596-624
+            c = self.sw.upper_matvec(self.mats["Vx_ut"], self.n + 1, c)
+        y = self.sw.lower_matvec(self.mats["Vx_lt"], c)
         if self.P is not None:
             out = np.empty_like(y)
             out[self.P] = y
@@ -208,4 +241,6 @@ class OracleTransform:
 
     # src/lpfun/transform.py:806-848
     def eval(self, coeffs, points):
+        if self.basis == "chebyshev":
+            return self.sw.eval_chebyshev(coeffs, points, self.n)
         return self.sw.eval(coeffs, self.x, points, self.n)

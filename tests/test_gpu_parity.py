@@ -86,6 +86,69 @@ def test_golden_case(T, name):
     tf.close()
 
 
+@pytest.mark.parametrize("name", golden_cases("chebyshev"))
+@pytest.mark.parametrize("generic", [0, 1])
+def test_golden_case_chebyshev(T, name, generic):
+    """basis="chebyshev": V = L U, fnt = lower sweep (inv(L) mat-vec or L solve) + upper sweep (inv(U) mat-vec
+    or U back-substitution, transform.py:491-548), ifnt = upper + lower mat-vec (:596-624), eval by the
+    T_k recurrence (utils.py:165-195).  Bit-exact except eval (tree-shaped sum) like the Newton cases."""
+    g = load_case(name)
+    t = make(T, g, exact_ifnt=True)
+    t.set_option("force_generic", generic)
+    m = int(g["m"])
+    assert t.basis == "chebyshev"
+    assert np.array_equal(t.multi_index_set, g["A"].astype(np.int64)) and np.array_equal(t.nodes, g["x"])
+    got = t.fnt(g["values"])
+    nbits = int(np.sum(got != g["fnt"]))
+    assert nbits == 0, f"{nbits} coefficients differ, rel {relmax(got, g['fnt']):.2e}"
+    assert np.array_equal(t.fnt(g["values"][0]), g["fnt"][0])
+    assert np.array_equal(t.fnt(g["rnd"]), g["fnt_rnd"])
+    assert np.array_equal(t.ifnt(g["fnt"]), g["ifnt"])
+    assert np.array_equal(t.ifnt(g["rnd"]), g["ifnt_rnd"])
+    tf = make(T, g)
+    tf.set_option("force_generic", generic)
+    assert relmax(tf.ifnt(g["fnt"]), g["ifnt"]) <= TOL_IFNT_FMA
+    inf_multi = np.isinf(float(g["p"])) and m > 1
+    for key in g.files:
+        if key.startswith("dx_"):
+            _, i, k = key.split("_")
+            out = t.dx(g["fnt"][0], int(i), int(k))
+            if inf_multi:
+                assert relmax(out, g[key]) <= 1e-13, key
+            else:
+                assert np.array_equal(out, g[key]), key
+        elif key.startswith("dxT_"):
+            _, i, k = key.split("_")
+            assert np.array_equal(t.dxT(g["rnd"], int(i), int(k)), g[key]), key
+    assert relmax(t.eval(g["fnt"][0], g["points"]), g["eval"]) <= TOL_EVAL
+    assert relmax(t.eval(g["dx_0_1"], g["points"]), g["eval_dx0"]) <= TOL_EVAL
+    # device-tensor path runs the same two sweeps back to back on the caller's stream
+    import torch
+
+    c = t.fnt(torch.as_tensor(g["values"], device="cuda"))
+    assert np.array_equal(c.cpu().numpy(), g["fnt"])
+    assert np.array_equal(t.ifnt(c).cpu().numpy(), g["ifnt"])
+    t.close()
+    tf.close()
+
+
+def test_chebyshev_vs_oracle_larger(T):
+    """Seeded inputs at a size no fixture holds: Transform(3, 24, basis="chebyshev"), both fnt variants."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(11)
+    for pre in (True, False):
+        t = T(3, 24, basis="chebyshev", precomputation=pre, report=False, exact_ifnt=True)
+        o = O.OracleTransform(3, 24, 2.0, precomputation=pre, basis="chebyshev")
+        v = rng.standard_normal((3, len(t)))
+        c = t.fnt(v)
+        assert np.array_equal(c, np.stack([o.fnt(r) for r in v]))
+        assert np.array_equal(t.ifnt(c), np.stack([o.ifnt(r) for r in c]))
+        pts = rng.uniform(-1, 1, (500, 3))
+        assert relmax(t.eval(c[0], pts), o.eval(c[0], pts)) <= TOL_EVAL
+        t.close()
+
+
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d2n7_inf", "d1n12", "d3n12_solve"])
 def test_generic_kernels_match_too(T, name):
     """force_generic routes every op through the unbounded-n fallback kernels."""

@@ -89,6 +89,14 @@ def test_chebyshev_matrices_bit_exact(name):
     L, Uu = U.get_lu(g["Vx"])
     assert np.array_equal(U.pack_lower(L), g["Vx_lt"])
     assert np.array_equal(U.pack_upper(Uu), g["Vx_ut"])
+    if g["inv_Vx_lt"].size:
+        assert np.array_equal(U.pack_lower(np.linalg.inv(L)), g["inv_Vx_lt"])
+        assert np.array_equal(U.pack_upper(np.linalg.inv(Uu)), g["inv_Vx_ut"])
+    D = g["Dx"]
+    for q, M in enumerate((D, D @ D, D @ (D @ D))):
+        assert np.array_equal(U.pack_upper(M), g[f"Dx_lt{q}"])
+        assert np.array_equal(U.pack_lower(M.T), g[f"DxT_lt{q}"])
+    assert not U.is_lower_triangular(g["Vx"]) and U.is_lower_triangular(D.T)
 
 
 def test_classify_errors():

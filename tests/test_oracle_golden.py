@@ -33,11 +33,15 @@ def _oracle_for(g):
         Dx_ut=[g[f"Dx_lt{q}"] for q in range(3)],
         DxT_lt=[g[f"DxT_lt{q}"] for q in range(3)],
     )
+    if g["Vx_ut"].size:  # LU-factorised V (Chebyshev basis)
+        mats["Vx_ut"] = g["Vx_ut"]
+        mats["inv_Vx_ut"] = g["inv_Vx_ut"] if g["inv_Vx_ut"].size else None
     return O.OracleTransform(int(g["m"]), int(g["n"]), float(g["p"]), nodes=str(g["nodes_kind"]),
-                             precomputation=bool(g["precomputation"]), colex_order=bool(g["colex"]), mats=mats)
+                             precomputation=bool(g["precomputation"]), colex_order=bool(g["colex"]), mats=mats,
+                             basis=str(g["basis"]))
 
 
-@pytest.mark.parametrize("name", golden_cases("newton"))
+@pytest.mark.parametrize("name", golden_cases())
 def test_oracle_bit_exact_vs_reference(name):
     g = load_case(name)
     t = _oracle_for(g)
