@@ -148,13 +148,14 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          "use_tiles" (0 = per-coordinate line/fibre kernels instead of the row-tile kernels),
  *          "use_pipe" (1 = persistent cp.async-pipelined row-tile kernels), "use_sorted" (1 = globally
  *          length-sorted per-coordinate kernels), "use_groups" (0 = natural lane order in the fibre kernel),
- *          "use_whole" (1 = whole-function-in-shared-memory kernel for m <= 3), "use_planes" (1 = coordinates
+ *          "use_whole" (whole function in shared memory, one pass over HBM per transform, m = 2, 3:
+ *          -1 = automatic (default), 0 = off, 1/2/3 = first / bulk-copy / box-layout generation), "use_planes" (1 = coordinates
  *          0 and 1 fused, one warp per plane), "use_two_lanes" (1 = two adjacent lanes per thread),
  *          "eval_block" (0 = non-staged eval kernel), "debug_skip" (development: skip the arithmetic),
  *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line
- * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4/5 row-tile sweep (5: fused with coordinate 0), 6/7 pipelined row-tile sweep (7: fused), 8 permutation) and its device time in ms.
+ * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4/5 row-tile sweep (5: fused with coordinate 0), 6/7 pipelined row-tile sweep (7: fused), 8 permutation, 9 sorted, 10/14/15 whole-function kernels, 11/12 eval, 13 planes) and its device time in ms.
  * Synchronises on the recorded events.  *count receives the number of records seen. */
 int lpfnt_plan_trace_read(lpfnt_plan *plan, int max_records, int *labels, float *ms, int *count);
 

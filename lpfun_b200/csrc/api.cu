@@ -87,8 +87,18 @@ struct lpfnt_plan {
     int use_tiles = 0;                       // row-tile kernels (sorted work items, fused coordinate 0); measured slower than the
                                              // per-coordinate kernels on B200 so far, kept selectable
     int debug_skip = 0;
-    int use_whole = 0;                       // m <= 3: whole function in shared memory, one pass per transform (selectable;
-                                             // measured on par with the per-coordinate kernels at d=3 n=30, slower for tiny N)
+    int use_whole = -1;                      // whole function in shared memory, ONE pass over HBM per transform (m = 2, 3):
+                                             // -1 auto (k_whole2 when its 768 threads are at least 2/3 busy: N_1 >= 512),
+                                             // 0 off, 1 k_whole, 2 k_whole2, 3 k_whole3 (box layout, producer warp)
+    // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
+    struct Box {
+        bool ok = false;
+        BoxConst c{};
+        int32_t n_box = 0, n_item[3] = {0, 0, 0}, max_t = 0;
+        uint32_t *d_item[3] = {nullptr, nullptr, nullptr};
+        int2 *d_pline = nullptr;
+        uint16_t *d_perm16 = nullptr, *d_line_off16 = nullptr;
+    } box;
     int use_two_lanes = 0;                   // two adjacent lanes per thread in the lane-group kernel
     int use_groups = 1;                      // height-ordered lane groups in the per-coordinate fibre kernel
     int use_sorted = 0;                      // globally length-sorted per-coordinate kernels (no shared memory)
@@ -330,8 +340,150 @@ int launch_perm(lpfnt_plan *p, const double *src, double *dst, int64_t batch, bo
 }
 
 // Whole-function path (m <= 3, everything of one function in shared memory): one launch per transform.
+// Box layout for k_whole3, built from A alone (any downward-closed set with m = 2 or 3).
+int build_box(lpfnt_plan *p, const int64_t *A, const int64_t *perm, const HostIndex &hx) {
+    const int m = p->m;
+    const int64_t N = p->N, N1 = p->N1;
+    if (m < 2 || m > 3 || N >= 65536 || N1 > kW3Compute || p->n + 1 > kMaxRegT) return LPFNT_OK;
+    // (a0, a1, k): m = 3 -> alpha; m = 2 -> (alpha_0, 0, alpha_1)
+    auto a1_of = [&](int64_t i) { return m == 3 ? int(A[i * m + 1]) : 0; };
+    auto k_of = [&](int64_t i) { return int(A[i * m + m - 1]); };
+    int K = 0;
+    for (int64_t i = 0; i < N; ++i) K = std::max(K, k_of(i) + 1);
+    if (K > 32) return LPFNT_OK;
+    std::vector<int> nl(K, 0), len0(K, 0);
+    for (int64_t i = 0; i < N; ++i) {
+        const int k = k_of(i);
+        nl[k] = std::max(nl[k], a1_of(i) + 1);
+        len0[k] = std::max(len0[k], int(A[i * m]) + 1);
+    }
+    lpfnt_plan::Box &B = p->box;
+    int64_t W = 0, L = 0;
+    for (int k = 0; k < 32; ++k) { B.c.P[k] = 0; B.c.S[k] = 0; B.c.L[k] = 0; }
+    for (int k = 0; k < K; ++k) {
+        B.c.P[k] = int32_t(W); B.c.S[k] = len0[k] | 1; B.c.L[k] = int32_t(L);
+        W += int64_t(nl[k]) * B.c.S[k];
+        L += nl[k];
+    }
+    if (L != N1 || W > 65535 || whole3_smem_bytes(int(W), int(N1), int(N), perm != nullptr) > size_t(227) * 1024) return LPFNT_OK;
+    std::vector<uint16_t> lo16(N1);
+    std::vector<int2> pline(N1);
+    // line lengths per (a1, k)
+    std::vector<std::vector<int>> len(K);
+    for (int k = 0; k < K; ++k) len[k].assign(nl[k], 0);
+    for (int64_t l = 0; l < N1; ++l) {
+        const int64_t i = hx.line_off[l];
+        lo16[l] = uint16_t(i);
+        if (B.c.L[k_of(i)] + a1_of(i) != l) return LPFNT_OK;  // lines are not plane-major (cannot happen for colex order)
+        len[k_of(i)][a1_of(i)] = int(hx.line_off[l + 1] - hx.line_off[l]);
+        pline[l] = make_int2(int(B.c.P[k_of(i)] + a1_of(i) * B.c.S[k_of(i)]) | (len[k_of(i)][a1_of(i)] << 16), int(i));
+    }
+    auto sort_desc = [](std::vector<std::pair<int, uint32_t>> &v, std::vector<uint32_t> &out) {
+        std::stable_sort(v.begin(), v.end(), [](const std::pair<int, uint32_t> &x, const std::pair<int, uint32_t> &y) { return x.first > y.first; });
+        out.resize(v.size());
+        for (size_t q = 0; q < v.size(); ++q) out[q] = v[q].second;
+    };
+    std::vector<std::pair<int, uint32_t>> tmp;
+    std::vector<uint32_t> item[3];
+    int max_t = 0;
+    // coordinate 0: lines
+    for (int k = 0; k < K; ++k)
+        for (int a1 = 0; a1 < nl[k]; ++a1) {
+            const int t = len[k][a1];
+            tmp.push_back({t, uint32_t(B.c.P[k] + a1 * B.c.S[k]) | (uint32_t(t) << 16)});
+            max_t = std::max(max_t, t);
+        }
+    sort_desc(tmp, item[0]);
+    // coordinate 1 (m = 3): (a0, k)
+    tmp.clear();
+    if (m == 3)
+        for (int k = 0; k < K; ++k)
+            for (int a0 = 0; a0 < len0[k]; ++a0) {
+                int t = 0;
+                while (t < nl[k] && len[k][t] > a0) ++t;
+                tmp.push_back({t, uint32_t(B.c.P[k] + a0) | (uint32_t(B.c.S[k]) << 16) | (uint32_t(t) << 24)});
+                max_t = std::max(max_t, t);
+            }
+    sort_desc(tmp, item[1]);
+    // last coordinate: (a0, a1) of plane 0
+    tmp.clear();
+    for (int a1 = 0; a1 < nl[0]; ++a1)
+        for (int a0 = 0; a0 < len[0][a1]; ++a0) {
+            int t = 0;
+            while (t < K && a1 < nl[t] && len[t][a1] > a0) ++t;
+            tmp.push_back({t, uint32_t(a0) | (uint32_t(a1) << 8) | (uint32_t(t) << 16)});
+            max_t = std::max(max_t, t);
+        }
+    sort_desc(tmp, item[2]);
+    for (int h = 0; h < 3; ++h) if (item[h].size() > size_t(kW3Compute)) return LPFNT_OK;
+    int rc;
+    for (int h = 0; h < 3; ++h) {
+        B.n_item[h] = int32_t(item[h].size());
+        if ((rc = upload(&B.d_item[h], item[h].data(), item[h].size(), p))) return rc;
+    }
+    if ((rc = upload(&B.d_pline, pline.data(), pline.size(), p))) return rc;
+    if ((rc = upload(&B.d_line_off16, lo16.data(), lo16.size(), p))) return rc;
+    if (perm) {
+        std::vector<uint16_t> p16(N);
+        for (int64_t i = 0; i < N; ++i) p16[i] = uint16_t(perm[i]);
+        if ((rc = upload(&B.d_perm16, p16.data(), p16.size(), p))) return rc;
+    }
+    B.n_box = int32_t(W); B.max_t = max_t; B.ok = true;
+    return LPFNT_OK;
+}
+
+bool whole3_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims) {
+    if (p->use_whole != 3 || p->force_generic || !p->box.ok || int(dims.size()) != p->m) return false;
+    for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
+    if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
+    return pick_cap(std::max(p->box.max_t, 1)) > 0;
+}
+
+int launch_whole3_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+    const int mode = sweep_mode(spec);
+    const int cap = pick_cap(std::max(p->box.max_t, 1));
+    std::vector<double> tri;
+    repack(spec.packed, p->n + 1, spec.kind, cap, tri);
+    const lpfnt_plan::Box &B = p->box;
+    Whole3Args a{};
+    a.item0 = B.d_item[0]; a.item1 = B.d_item[1]; a.item2 = B.d_item[2];
+    a.pline = B.d_pline; a.perm16 = B.d_perm16; a.line_off16 = B.d_line_off16;
+    a.gather = gather ? 1 : 0; a.scatter = scatter ? 1 : 0;
+    a.n_elem = int32_t(p->N); a.n_box = B.n_box; a.n_lines = int32_t(p->N1); a.m = p->m;
+    a.n_item0 = B.n_item[0]; a.n_item1 = B.n_item[1]; a.n_item2 = B.n_item[2];
+    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
+        const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
+        a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
+        const int grid = int(std::min<int64_t>(nb, p->num_sms));
+        cudaError_t e = cudaSuccess;
+        trace_begin(p, 1500, s);
+        switch (cap) {
+            case 8: e = launch_whole3<8>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
+            case 16: e = launch_whole3<16>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
+            case 24: e = launch_whole3<24>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
+            default: e = launch_whole3<32>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
+        }
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("whole-function (box) kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    }
+    return LPFNT_OK;
+}
+
+// second-generation whole-function kernel: every sweep in one round, bulk copies need 16-byte granules
+bool whole2_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in) {
+    const bool want = p->use_whole == 2 || (p->use_whole == -1 && p->N1 >= 512);
+    if (!want || p->force_generic || p->m < 2 || p->m > 3 || int(dims.size()) != p->m) return false;
+    for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
+    if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
+    if (p->N >= 65536 || (p->N & 1) || p->N1 > kWhole2Threads || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return false;
+    for (int h = 1; h < p->m; ++h) if (!p->dd[h].sorted || !p->dd[h].ent_off16 || p->dd[h].num_sorted != p->N1) return false;
+    return whole2_smem_bytes(int(p->N), int(p->N1)) <= size_t(227) * 1024;
+}
+
 bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims) {
-    if (!p->use_whole || p->force_generic || p->m > 3 || int(dims.size()) != p->m) return false;
+    if (p->use_whole != 1 || p->force_generic || p->m > 3 || int(dims.size()) != p->m) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
     if (spec.kind != LPFNT_LOWER) return false;
     if (p->N >= 65536 || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
@@ -339,7 +491,7 @@ bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int>
     return whole_smem_bytes(int(p->N), int(p->N1)) <= size_t(220) * 1024;
 }
 
-int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s, bool gen2 = false) {
     const int n1 = p->n + 1;
     const int mode = sweep_mode(spec);
     int len = p->max_line;
@@ -361,9 +513,17 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
         a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
-        const int grid = int(std::min<int64_t>(nb, int64_t(p->num_sms) * occ));
+        const int grid = int(std::min<int64_t>(nb, int64_t(p->num_sms) * (gen2 ? 1 : occ)));
         cudaError_t e = cudaSuccess;
-        trace_begin(p, 1000, s);
+        trace_begin(p, gen2 ? 1400 : 1000, s);
+        if (gen2) {
+            switch (cap) {
+                case 8: e = launch_whole2<8>(mode, spec.fma, a, tri.data(), grid, s); break;
+                case 16: e = launch_whole2<16>(mode, spec.fma, a, tri.data(), grid, s); break;
+                case 24: e = launch_whole2<24>(mode, spec.fma, a, tri.data(), grid, s); break;
+                default: e = launch_whole2<32>(mode, spec.fma, a, tri.data(), grid, s); break;
+            }
+        } else
         switch (cap) {
             case 8: e = launch_whole<8>(mode, spec.fma, a, tri.data(), grid, s); break;
             case 16: e = launch_whole<16>(mode, spec.fma, a, tri.data(), grid, s); break;
@@ -396,6 +556,14 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
         return LPFNT_EUNSUPPORTED;
     }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
+    if (whole3_ok(p, spec, dims)) {
+        // in-place is safe: a function is complete in shared memory / registers before its first store
+        return launch_whole3_fn(p, spec, in, out, batch, gather, scatter, s);
+    }
+    if (whole2_ok(p, spec, dims, in)) {
+        // in-place is safe: a function is complete in shared memory / registers before its first store
+        return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s, true);
+    }
     if (whole_ok(p, spec, dims)) {
         // in-place is safe: a function is read completely into shared memory before it is written
         return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s);
@@ -655,6 +823,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
             p->num_planes = D1.num_fibres;
         }
     }
+    if ((rc = build_box(p, A, perm, hx))) return fail(rc);
     if (!hx.sorted0.empty())
         if ((rc = upload(&p->d_sorted0, reinterpret_cast<const int2 *>(hx.sorted0.data()), hx.sorted0.size(), p))) return fail(rc);
     if (!hx.eval_block.empty()) {
@@ -688,6 +857,8 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
+    for (int h = 0; h < 3; ++h) cudaFree(p->box.d_item[h]);
+    cudaFree(p->box.d_pline); cudaFree(p->box.d_perm16); cudaFree(p->box.d_line_off16);
     cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_sorted0); cudaFree(p->d_plane_line); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
@@ -715,7 +886,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_planes") == 0) { p->use_planes = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < -1 ? -1 : (value > 3 ? 3 : value); return LPFNT_OK; }
     if (std::strcmp(name, "use_two_lanes") == 0) { p->use_two_lanes = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_sorted") == 0) { p->use_sorted = value ? 1 : 0; return LPFNT_OK; }

@@ -152,6 +152,62 @@ cudaError_t launch_whole<T>(int mode, bool fma, const WholeArgs &a, const double
 
 namespace {
 template <int MODE, bool FMA>
+cudaError_t whole2_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, cudaStream_t s) {
+    auto kern = k_whole2<T, MODE, FMA, kWhole2Threads>;
+    const size_t smem = whole2_smem_bytes(a.n_elem, a.n_lines);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, kWhole2Threads, smem, s>>>(a, M);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <>
+cudaError_t launch_whole2<T>(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? whole2_launch<kLowerMatvec, true>(a, M, grid, s) : whole2_launch<kLowerMatvec, false>(a, M, grid, s);
+        case kUpperMatvec: return fma ? whole2_launch<kUpperMatvec, true>(a, M, grid, s) : whole2_launch<kUpperMatvec, false>(a, M, grid, s);
+        case kLowerSolve: return whole2_launch<kLowerSolve, false>(a, M, grid, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+namespace {
+template <int MODE, bool FMA>
+cudaError_t whole3_launch(const Whole3Args &a, const BoxConst &c, const PackedTri<T> &M, int grid, cudaStream_t s) {
+    auto kern = k_whole3<T, MODE, FMA>;
+    const size_t smem = whole3_smem_bytes(a.n_box, a.n_lines, a.n_elem, a.perm16 != nullptr);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, kW3Threads, smem, s>>>(a, M, c);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <>
+cudaError_t launch_whole3<T>(int mode, bool fma, const Whole3Args &a, const BoxConst &c, const double *tri, int grid, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec: return fma ? whole3_launch<kLowerMatvec, true>(a, c, M, grid, s) : whole3_launch<kLowerMatvec, false>(a, c, M, grid, s);
+        case kUpperMatvec: return fma ? whole3_launch<kUpperMatvec, true>(a, c, M, grid, s) : whole3_launch<kUpperMatvec, false>(a, c, M, grid, s);
+        case kLowerSolve: return whole3_launch<kLowerSolve, false>(a, c, M, grid, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+namespace {
+template <int MODE, bool FMA>
 cudaError_t plane_launch(const PlaneSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
     dim3 grid((a.num_planes + 3) / 4, batch);
     k_sweep_planes<T, MODE, FMA><<<grid, 128, 0, s>>>(a, M);

@@ -59,36 +59,35 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 
 // Apply the triangular operator to a register-resident fibre of length t, in place.
-template <int MAXT, int MODE, bool FMA>
+// ROWS = output rows folded side by side in the lower mat-vec (independent accumulators).
+template <int MAXT, int MODE, bool FMA, int ROWS = 4>
 __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M) {
     if constexpr (MODE == kLowerMatvec) {
         // Outputs from the top down: out_k only reads x_j, j <= k, so it may overwrite x_k.
-        // FOUR rows are folded side by side (independent accumulators): the sweeps are latency
-        // bound (ncu: "wait" is the top stall at 20 warps/SM), and four chains per thread hide the
-        // 8.4-cycle DADD/DFMA latency twice as well as two; each row keeps its own ascending-j order.
+        // ROWS rows are folded side by side (independent accumulators): the sweeps are latency
+        // bound (ncu: "wait" is the top stall at 20 warps/SM), and several chains per thread hide the
+        // 8.4-cycle DADD/DFMA latency; each row keeps its own ascending-j order.
         // Rows of a block that lie beyond the fibre (k >= t) are computed on zeros and never stored.
-        static_assert(MAXT % 4 == 0, "rows are processed in blocks of four");
+        static_assert(MAXT % ROWS == 0, "rows are processed in blocks of ROWS");
 #pragma unroll
-        for (int k = MAXT - 1; k >= 3; k -= 4) {
-            if (k - 3 < t) {
-                double a3 = 0.0, a2 = 0.0, a1 = 0.0, a0 = 0.0;
+        for (int k = MAXT - 1; k >= ROWS - 1; k -= ROWS) {
+            if (k - (ROWS - 1) < t) {
+                double acc[ROWS];
 #pragma unroll
-                for (int j = 0; j <= k - 3; ++j) {
-                    a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + j], x[j]);
-                    a2 = mac<FMA>(a2, M.v[(k - 1) * k / 2 + j], x[j]);
-                    a1 = mac<FMA>(a1, M.v[(k - 2) * (k - 1) / 2 + j], x[j]);
-                    a0 = mac<FMA>(a0, M.v[(k - 3) * (k - 2) / 2 + j], x[j]);
+                for (int r = 0; r < ROWS; ++r) acc[r] = 0.0;
+#pragma unroll
+                for (int j = 0; j <= k - (ROWS - 1); ++j) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) acc[r] = mac<FMA>(acc[r], M.v[(k - r) * (k - r + 1) / 2 + j], x[j]);
                 }
-                a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + k - 2], x[k - 2]);
-                a2 = mac<FMA>(a2, M.v[(k - 1) * k / 2 + k - 2], x[k - 2]);
-                a1 = mac<FMA>(a1, M.v[(k - 2) * (k - 1) / 2 + k - 2], x[k - 2]);
-                a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + k - 1], x[k - 1]);
-                a2 = mac<FMA>(a2, M.v[(k - 1) * k / 2 + k - 1], x[k - 1]);
-                a3 = mac<FMA>(a3, M.v[k * (k + 1) / 2 + k], x[k]);
-                x[k] = a3;
-                x[k - 1] = a2;
-                x[k - 2] = a1;
-                x[k - 3] = a0;
+#pragma unroll
+                for (int j = k - (ROWS - 1) + 1; j <= k; ++j) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r)
+                        if (r <= k - j) acc[r] = mac<FMA>(acc[r], M.v[(k - r) * (k - r + 1) / 2 + j], x[j]);
+                }
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) x[k - r] = acc[r];
             }
         }
     } else if constexpr (MODE == kUpperMatvec) {
@@ -831,6 +830,298 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole(const WholeArgs a, const _
         } else {
 #pragma unroll 4
             for (int i = tid; i < N; i += THREADS) out[i] = buf[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole-function kernel, second generation (m = 2, 3; N_1 <= THREADS): ONE pass over HBM per transform.
+//
+//   * persistent: one CTA per SM, 768 threads; the CTA walks over its share of the functions;
+//   * the function (N doubles, contiguous in HBM) arrives in shared memory by the bulk-copy
+//     engine (cp.async.bulk + mbarrier), no thread touches a load instruction for it;
+//   * every sweep is ONE round: thread <-> item (line for coordinate 0, element-fibre otherwise),
+//     items in length order so that warps are uniform; coordinates 0 .. m-2 work in place in
+//     shared memory;
+//   * the LAST coordinate reads its fibres into registers, then the buffer is free: one thread
+//     issues the bulk copy of the CTA's NEXT function while everybody computes the last sweep
+//     and stores the result from registers straight to HBM (fused colex scatter).  The load of
+//     function k+1 therefore overlaps the last third of the arithmetic of function k, and the
+//     FP64 pipe only idles at the four barriers per function.
+// Algorithmic traffic = actual traffic = 16 B/DOF per transform.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gsrc), "r"(bytes), "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kWhole2Threads = 768;
+constexpr unsigned kBulkPiece = 32768;  // bytes per bulk-copy instruction
+
+template <int MAXT, int MODE, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = a.n_elem, N1 = a.n_lines, m = a.m;
+    const int Npad = (N + 1) & ~1;
+    double *buf = reinterpret_cast<double *>(smem_raw);                    // [Npad]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(buf + Npad);              // one mbarrier
+    int2 *sitem = reinterpret_cast<int2 *>(bar + 2);                       // [m][N1]: {eo index | t << 24, element offset added}
+    uint16_t *seo = reinterpret_cast<uint16_t *>(sitem + 3 * N1);          // [32 identity][N1 coordinate 1][N1 coordinate 2]
+    const int tid = threadIdx.x;
+
+    // One addressing form for every coordinate: element k of an item sits at seo[p + k] + add (see k_whole).
+    if (tid < 32) seo[tid] = static_cast<uint16_t>(tid);
+    for (int h = 0; h < m; ++h) {
+        for (int i = tid; i < N1; i += THREADS) {
+            const int2 it = __ldg(a.sorted[h] + i);
+            const int t = it.y >> 8;
+            if (h == 0) sitem[i] = make_int2(t << 24, it.x);
+            else {
+                sitem[h * N1 + i] = make_int2((32 + (h - 1) * N1 + it.x) | (t << 24), it.y & 0xff);
+                seo[32 + (h - 1) * N1 + i] = __ldg(a.ent_off[h] + i);
+            }
+        }
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned fbytes = unsigned(N) * 8u;  // multiple of 16 (host checks N even)
+    auto issue_load = [&](int b) {
+        const char *src = reinterpret_cast<const char *>(a.in + int64_t(b) * N);
+        mbar_expect_tx(bar, fbytes);
+        for (unsigned o = 0; o < fbytes; o += kBulkPiece)
+            bulk_g2s(reinterpret_cast<char *>(buf) + o, src + o, min(kBulkPiece, fbytes - o), bar);
+    };
+    if (tid == 0 && int(blockIdx.x) < a.batch) issue_load(blockIdx.x);
+    unsigned parity = 0;
+
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        double *out = a.out + int64_t(b) * N;
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll 1
+        for (int h = 0; h < m; ++h) {
+            int t = 0, add = 0;
+            const uint16_t *eo = seo;
+            if (tid < N1) { const int2 it = sitem[h * N1 + tid]; t = int(unsigned(it.x) >> 24); eo = seo + (it.x & 0xffffff); add = it.y; }
+            const bool last = (h == m - 1);
+            double x[MAXT];
+            if (h == 0 && a.perm_in) {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[__ldg(a.perm_in + add + k)] : 0.0;
+                __syncthreads();  // the gather reads other lines' slots: nobody writes before everybody has read
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[eo[k] + add] : 0.0;
+            }
+            if (last) {
+                // every thread holds its fibre in registers: the buffer is free for the next function
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0 && b + int(gridDim.x) < a.batch) issue_load(b + gridDim.x);
+            }
+            apply_fibre<MAXT, MODE, FMA>(x, t, M);
+            if (last) {
+                if (a.perm_out) {
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) out[__ldg(a.perm_out + eo[k] + add)] = x[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) out[eo[k] + add] = x[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k)
+                    if (k < t) buf[eo[k] + add] = x[k];
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole-function kernel, third generation ("box" layout; m = 2, 3): ONE pass over HBM per
+// transform, no offset look-ups, producer warps.
+//
+// Shared-memory layout of a function: plane k (= alpha_2; for m = 2 every line is its own plane)
+// is a rectangle of nl[k] rows with an ODD row stride S[k] >= longest line of the plane:
+//       addr(a0, a1, k) = P[k] + a1 * S[k] + a0           (P, S: kernel constants, BoxConst)
+// so a fibre along coordinate 1 is a constant-stride walk, a fibre along coordinate 2 needs only
+// the constants, and the lines of one plane (coordinate 0, thread <-> line) fall into different
+// banks.  ~4/pi of the compact size for an l^2 ball (152 KB at d=3, n=30).
+//
+// Thread roles: 736 compute threads (23 warps), thread <-> one item per sweep, items in length
+// order (uniform warps); 2 producer warps copy the CTA's NEXT function from HBM into the box
+// (cp.async 8 B, colex gather applied on the way) while the compute warps run the last sweep
+// from registers and store its result straight to HBM (colex scatter applied on the way).
+// Named barriers: FULL (producers -> compute), EMPTY (compute -> producers), STEP (compute only).
+// ---------------------------------------------------------------------------------------
+struct BoxConst {
+    int32_t P[32];  // first element of plane k in the box
+    int32_t S[32];  // row stride of plane k
+    int32_t L[32];  // first line of plane k in the compact (HBM) order
+};
+
+struct Whole3Args {
+    const double *in;
+    double *out;
+    const uint32_t *item0;   // lines:               box base | t << 16
+    const uint32_t *item1;   // (a0, k) fibres:      box base | stride << 16 | t << 24        (m = 3 only)
+    const uint32_t *item2;   // (a0, a1) fibres:     a0 | a1 << 8 | t << 16
+    const int2 *pline;       // per line (compact order): {box base | t << 16, compact offset}
+    const uint16_t *perm16;  // colex permutation (or nullptr)
+    const uint16_t *line_off16;  // compact offset of every line
+    int32_t gather, scatter;
+    int32_t n_elem, n_box, n_lines, m, batch;
+    int32_t n_item0, n_item1, n_item2;
+};
+
+constexpr int kW3Compute = 736;
+constexpr int kW3Producer = 32;
+inline size_t whole3_smem_bytes(int n_box, int n_lines, int n_elem, bool perm) {
+    return size_t(n_box) * 8 + size_t(3) * kW3Compute * 4 + size_t(n_lines) * 8 + size_t((n_lines + 1) & ~1) * 2 + (perm ? size_t(n_elem + 8) * 2 : 0) + 16;
+}
+constexpr int kW3Threads = kW3Compute + kW3Producer;
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int MAXT, int MODE, bool FMA>
+__global__ void __launch_bounds__(kW3Threads, 1)
+k_whole3(const Whole3Args a, const __grid_constant__ PackedTri<MAXT> M, const __grid_constant__ BoxConst C) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *buf = reinterpret_cast<double *>(smem_raw);                 // [n_box]
+    unsigned *sitem = reinterpret_cast<unsigned *>(buf + a.n_box);      // [3][kW3Compute] item words (0 = idle)
+    int2 *spline = reinterpret_cast<int2 *>(sitem + 3 * kW3Compute);    // [n_lines] producer's line descriptors
+    uint16_t *soff = reinterpret_cast<uint16_t *>(spline + a.n_lines);  // [n_lines (+1 if odd)]
+    uint16_t *sperm = soff + ((a.n_lines + 1) & ~1);                    // [n_elem] colex permutation (if any)
+    const int tid = threadIdx.x;
+    const int N = a.n_elem;
+    constexpr int FULL = 1, EMPTY = 2, STEP = 3;
+
+    for (int i = tid; i < a.n_lines; i += kW3Threads) {
+        soff[i] = __ldg(a.line_off16 + i);
+        spline[i] = __ldg(a.pline + i);
+    }
+    if (a.perm16)
+        for (int i = tid; i < N; i += kW3Threads) sperm[i] = __ldg(a.perm16 + i);
+    if (tid < kW3Compute) {
+        sitem[tid] = tid < a.n_item0 ? __ldg(a.item0 + tid) : 0u;
+        sitem[kW3Compute + tid] = (a.m == 3 && tid < a.n_item1) ? __ldg(a.item1 + tid) : 0u;
+        sitem[2 * kW3Compute + tid] = tid < a.n_item2 ? __ldg(a.item2 + tid) : 0u;
+    }
+    __syncthreads();
+
+    if (tid >= kW3Compute) {
+        // ---------------- producer warp: one coalesced cp.async per line ----------------
+        const int lane = tid - kW3Compute;
+        bool first = true;
+        for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+            if (!first) named_sync(EMPTY, kW3Threads);  // the compute warps hold function b - grid in registers
+            first = false;
+            const double *in = a.in + int64_t(b) * N;
+#pragma unroll 4
+            for (int l = 0; l < a.n_lines; ++l) {
+                const int2 d = spline[l];  // {box base | t << 16, compact offset}
+                if (lane < (d.x >> 16)) {
+                    int src = d.y + lane;
+                    if (a.gather) src = sperm[src];
+                    cp_async8(buf + (d.x & 0xffff) + lane, in + src);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait_all();
+            named_arrive(FULL, kW3Threads);
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    // The item words live in shared memory and are read again after the triangle code: nothing but
+    // the fibre itself stays in registers across apply_fibre (80 registers per thread at 768 threads).
+    const volatile unsigned *my_item = sitem + tid;
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        named_sync(FULL, kW3Threads);
+#pragma unroll 1
+        for (int h = 0; h < 3; ++h) {
+            if (h == 1 && a.m == 2) continue;
+            double x[MAXT];
+            int t;
+            {
+                const unsigned it = my_item[h * kW3Compute];
+                if (h < 2) {
+                    // coordinate 0: thread <-> line (stride 1); coordinate 1: thread <-> (a0, k), constant stride
+                    t = (h == 0) ? int(it >> 16) : int(it >> 24);
+                    const int st = (h == 0) ? 1 : int((it >> 16) & 0xff);
+                    const double *q = buf + (it & 0xffff);
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k) {
+                        x[k] = (k < t) ? *q : 0.0;
+                        q += st;
+                    }
+                } else {
+                    // last coordinate: thread <-> (a0, a1); planes through the constants
+                    t = int(it >> 16);
+                    const int a0 = int(it & 0xff), a1 = int((it >> 8) & 0xff);
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[C.P[k] + a1 * C.S[k] + a0] : 0.0;
+                    // the function now lives in registers: hand the box to the producers
+                    if (b + int(gridDim.x) < a.batch) named_arrive(EMPTY, kW3Threads);
+                }
+            }
+            apply_fibre<MAXT, MODE, FMA, FMA ? 4 : 2>(x, t, M);
+            const unsigned it = my_item[h * kW3Compute];
+            if (h < 2) {
+                const int st = (h == 0) ? 1 : int((it >> 16) & 0xff);
+                double *p = buf + (it & 0xffff);
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) {
+                    if (k < t) *p = x[k];
+                    p += st;
+                }
+                named_sync(STEP, kW3Compute);
+            } else {
+                double *out = a.out + int64_t(b) * N;
+                const int a0 = int(it & 0xff), a1 = int((it >> 8) & 0xff);
+                if (a.scatter) {
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) out[sperm[int(soff[C.L[k] + a1]) + a0]] = x[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) out[int(soff[C.L[k] + a1]) + a0] = x[k];
+                }
+            }
         }
     }
 }

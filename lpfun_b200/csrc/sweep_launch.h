@@ -36,6 +36,15 @@ inline size_t whole_smem_bytes(int n_elem, int n_lines) {
 }
 template <int MAXT>
 cudaError_t launch_whole(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s);
+// second generation (bulk-copy prefetch, one round per sweep, result stored from registers)
+inline size_t whole2_smem_bytes(int n_elem, int n_lines) {
+    return size_t((n_elem + 1) & ~1) * sizeof(double) + 16 + size_t(3) * n_lines * sizeof(int2) + (size_t(32) + 2 * size_t(n_lines)) * sizeof(uint16_t) + 16;
+}
+// third generation (box layout, producer warps)
+template <int MAXT>
+cudaError_t launch_whole3(int mode, bool fma, const Whole3Args &a, const BoxConst &c, const double *tri, int grid, cudaStream_t s);
+template <int MAXT>
+cudaError_t launch_whole2(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s);
 
 template <int MAXT>
 cudaError_t launch_plane_sweep(int mode, bool fma, const PlaneSweepArgs &a, const double *tri, int batch, cudaStream_t s);

@@ -149,6 +149,23 @@ def test_chebyshev_vs_oracle_larger(T):
         t.close()
 
 
+@pytest.mark.parametrize("whole", [2, 3])
+@pytest.mark.parametrize("name", ["d3n7_cheb", "d2n8_cheb", "d2n6_inf_cheb", "d3n7_cheb_solve", "d3n6_inf", "c1_d2n10", "d3n12_p1", "d3n9_p05"])
+def test_whole_function_kernels_more_shapes(T, name, whole):
+    """The one-pass whole-function kernels (bulk-copy k_whole2, box-layout k_whole3) on upper-triangular
+    sweeps (Chebyshev), p = inf / 1 / 0.5 sets and m = 2; batched so that every CTA loops over several functions."""
+    g = load_case(name)
+    t = make(T, g, exact_ifnt=True)
+    t.set_option("use_whole", whole)
+    reps = 40
+    got = t.fnt(np.tile(g["values"], (reps, 1)))
+    assert np.array_equal(got, np.tile(g["fnt"], (reps, 1)))
+    back = t.ifnt(np.tile(g["fnt"], (reps, 1)))
+    assert np.array_equal(back, np.tile(g["ifnt"], (reps, 1)))
+    assert np.array_equal(t.fnt(g["rnd"]), g["fnt_rnd"])
+    t.close()
+
+
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d2n7_inf", "d1n12", "d3n12_solve"])
 def test_generic_kernels_match_too(T, name):
     """force_generic routes every op through the unbounded-n fallback kernels."""
@@ -371,6 +388,9 @@ def test_c5_dx_eval_vs_oracle(T):
     {"use_whole": 1},
     {"use_whole": 0, "use_planes": 1},
     {"use_whole": 0, "use_two_lanes": 1},
+    {"use_whole": 2},
+    {"use_whole": 3},
+    {},
 ])
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d6n4", "d2n7_inf", "d3n12_solve", "c4_d3n30"])
 def test_alternative_kernel_families(T, name, opts):
