@@ -149,7 +149,8 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          "use_pipe" (1 = persistent cp.async-pipelined row-tile kernels), "use_sorted" (1 = globally
  *          length-sorted per-coordinate kernels), "use_groups" (0 = natural lane order in the fibre kernel),
  *          "use_whole" (whole function in shared memory, one pass over HBM per transform, m = 2, 3:
- *          -1 = automatic (default), 0 = off, 1/2/3 = first / bulk-copy / box-layout generation), "use_planes" (1 = coordinates
+ *          -1 = automatic (default), 0 = off, 1/2/3 = first / bulk-copy / box-layout generation), "use_slab" (coordinates 0 and 1 in one pass over
+ *          slabs of planes, any m >= 2: 1 = when the slabs fill the CTA (default), 0 = off, 2 = always), "use_planes" (1 = coordinates
  *          0 and 1 fused, one warp per plane), "use_two_lanes" (1 = two adjacent lanes per thread),
  *          "eval_block" (0 = non-staged eval kernel), "debug_skip" (development: skip the arithmetic),
  *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */

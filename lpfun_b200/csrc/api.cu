@@ -90,6 +90,14 @@ struct lpfnt_plan {
     int use_whole = -1;                      // whole function in shared memory, ONE pass over HBM per transform (m = 2, 3):
                                              // -1 auto (k_whole2 when its 768 threads are at least 2/3 busy: N_1 >= 512),
                                              // 0 off, 1 k_whole, 2 k_whole2, 3 k_whole3 (box layout, producer warp)
+    // slab kernel (coordinates 0 and 1 in one pass, any m >= 2; see k_slab)
+    struct Slabs {
+        bool ok = false;
+        int32_t n_slabs = 0, max_t = 0;
+        SlabDesc *d_desc = nullptr;
+        int2 *d_item0 = nullptr, *d_item1 = nullptr;
+    } slabs;
+    int use_slab = 1;
     // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
     struct Box {
         bool ok = false;
@@ -184,6 +192,8 @@ int sweep_mode(const SweepSpec &s) {
     return s.solve ? kUpperSolve : kUpperMatvec;
 }
 
+int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s);
+
 // One sweep along coordinate h: src -> dst (device pointers, may alias when no perm is used).
 int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const double *src, double *dst, int64_t batch,
                bool gather, bool scatter, cudaStream_t s) {
@@ -191,6 +201,9 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
     int mode = sweep_mode(spec);
     if (mode == kUpperSolve && h >= 1) mode = kUpperSolveDesc;  // the reference's fold order there (atoms.py:391-402)
     const int len = (h == 0) ? p->max_line : std::max(p->dd[h].max_lines, fuse0 ? p->max_line : 0);
+    const bool slab_ok = p->use_slab && p->slabs.ok && !p->force_generic && !p->use_tiles && !p->use_planes && !p->use_sorted &&
+                         pick_cap(std::max(p->slabs.max_t, 1)) > 0 && !(spec.solve && spec.kind == LPFNT_UPPER);
+    if (fuse0 && h == 1 && slab_ok) return launch_slab_pass(p, spec, src, dst, batch, gather, scatter, s);
     const bool planes = fuse0 && h == 1 && p->use_planes && p->num_planes > 0;
     const bool tiles = !planes && h >= 1 && p->use_tiles && !p->use_sorted && p->dd[h].num_tiles > 0;
     if (fuse0 && !tiles && !planes) { set_error("internal: fused coordinate-0 sweep needs the tile kernel"); return LPFNT_EINVAL; }
@@ -340,6 +353,101 @@ int launch_perm(lpfnt_plan *p, const double *src, double *dst, int64_t batch, bo
 }
 
 // Whole-function path (m <= 3, everything of one function in shared memory): one launch per transform.
+// Slab tables for k_slab: runs of consecutive planes (= fibres of coordinate 1) with at most
+// kSlabThreads lines, kSlabThreads coordinate-1 element-fibres and kSlabElems elements.
+int build_slabs(lpfnt_plan *p, const HostIndex &hx) {
+    if (p->m < 2 || hx.max_line > kMaxRegT || hx.dims[1].max_lines > kMaxRegT) return LPFNT_OK;
+    const DimTable &D = hx.dims[1];
+    for (int32_t f = 0; f < D.num_fibres; ++f)
+        for (int32_t r = D.fib_ptr[f]; r < D.fib_ptr[f + 1]; ++r)
+            if (D.ent[r].off != hx.line_off[r]) return LPFNT_OK;  // planes are not runs of consecutive lines
+    std::vector<SlabDesc> desc;
+    std::vector<int2> item0(hx.N1), item1;
+    item1.reserve(size_t(D.num_threads));
+    int max_t = 0;
+    int32_t f = 0;
+    while (f < D.num_fibres) {
+        int32_t f1 = f, nl = 0, nc = 0, ne = 0;
+        while (f1 < D.num_fibres) {
+            const int32_t pl = D.fib_ptr[f1 + 1] - D.fib_ptr[f1];
+            const int32_t pc = D.thr_start[f1 + 1] - D.thr_start[f1];
+            const int32_t pe = hx.line_off[D.fib_ptr[f1 + 1]] - hx.line_off[D.fib_ptr[f1]];
+            if (f1 > f && (nl + pl > kSlabThreads || nc + pc > kSlabThreads || ne + pe > kSlabElems)) break;
+            nl += pl; nc += pc; ne += pe; ++f1;
+        }
+        if (nl > kSlabThreads || nc > kSlabThreads || ne > kSlabElems) return LPFNT_OK;  // one plane alone is too big
+        SlabDesc d{};
+        d.l0 = D.fib_ptr[f]; d.nl = nl;
+        d.e0 = hx.line_off[d.l0]; d.ne = ne;
+        d.c0 = int32_t(item1.size()); d.nc = nc;
+        // coordinate 0: the slab's lines, longest first
+        std::vector<std::pair<int, int2>> tmp;
+        for (int32_t l = d.l0; l < d.l0 + nl; ++l) {
+            const int t = hx.line_off[l + 1] - hx.line_off[l];
+            tmp.push_back({t, make_int2(t << 24, hx.line_off[l] - d.e0)});
+            max_t = std::max(max_t, t);
+        }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first > y.first; });
+        for (int32_t q = 0; q < nl; ++q) item0[d.l0 + q] = tmp[q].second;
+        // coordinate 1: (plane, lane) element-fibres, longest first
+        tmp.clear();
+        for (int32_t g = f; g < f1; ++g) {
+            const int32_t p0 = D.fib_ptr[g], pl = D.fib_ptr[g + 1] - p0;
+            const int32_t lanes = D.thr_start[g + 1] - D.thr_start[g];
+            for (int32_t lane = 0; lane < lanes; ++lane) {
+                int t = 0;
+                while (t < pl && D.ent[p0 + t].len > lane) ++t;
+                tmp.push_back({t, make_int2((32 + (p0 - d.l0)) | (t << 24), lane)});
+                max_t = std::max(max_t, t);
+            }
+        }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first > y.first; });
+        for (auto &e : tmp) item1.push_back(e.second);
+        desc.push_back(d);
+        f = f1;
+    }
+    int rc;
+    lpfnt_plan::Slabs &S = p->slabs;
+    if ((rc = upload(&S.d_desc, desc.data(), desc.size(), p))) return rc;
+    if ((rc = upload(&S.d_item0, item0.data(), item0.size(), p))) return rc;
+    if ((rc = upload(&S.d_item1, item1.data(), item1.size(), p))) return rc;
+    S.n_slabs = int32_t(desc.size()); S.max_t = max_t;
+    // worth it only when the slabs keep the CTA busy (a 2-D function is ONE small plane: 31 lines at n = 30)
+    S.ok = hx.N1 / int64_t(desc.size()) >= kSlabThreads / 2;
+    return LPFNT_OK;
+}
+
+// One pass for coordinates 0 and 1 (k_slab): src -> dst.
+int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+    const int mode = sweep_mode(spec);
+    const int cap = pick_cap(std::max(p->slabs.max_t, 1));
+    std::vector<double> tri;
+    repack(spec.packed, p->n + 1, spec.kind, cap, tri);
+    SlabArgs a{};
+    a.slab = p->slabs.d_desc; a.item0 = p->slabs.d_item0; a.item1 = p->slabs.d_item1; a.line_off = p->d_line_off;
+    a.perm_in = gather ? p->d_perm : nullptr;
+    a.perm_out = scatter ? p->d_perm : nullptr;
+    a.stride = p->N; a.n_slabs = p->slabs.n_slabs;
+    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 24)) {
+        const int nb = int(std::min<int64_t>(int64_t(1) << 24, batch - b0));
+        a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
+        const int64_t units = int64_t(a.n_slabs) * nb;
+        const int grid = int(std::min<int64_t>(units, int64_t(p->num_sms) * 3));
+        cudaError_t e = cudaSuccess;
+        trace_begin(p, 1601, s);
+        switch (cap) {
+            case 8: e = launch_slab<8>(mode, spec.fma, a, tri.data(), grid, s); break;
+            case 16: e = launch_slab<16>(mode, spec.fma, a, tri.data(), grid, s); break;
+            case 24: e = launch_slab<24>(mode, spec.fma, a, tri.data(), grid, s); break;
+            default: e = launch_slab<32>(mode, spec.fma, a, tri.data(), grid, s); break;
+        }
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("slab kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    }
+    return LPFNT_OK;
+}
+
 // Box layout for k_whole3, built from A alone (any downward-closed set with m = 2 or 3).
 int build_box(lpfnt_plan *p, const int64_t *A, const int64_t *perm, const HostIndex &hx) {
     const int m = p->m;
@@ -572,7 +680,9 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     {
         size_t q = 0;
         const bool can_plane = !p->force_generic && p->use_planes && p->num_planes > 0 && pick_cap(std::max(p->max_line, p->dd[1].max_lines)) > 0;
-        const bool can_tile = can_plane || !p->force_generic && !p->use_sorted && p->use_tiles && p->m >= 2 && p->dd[1].num_tiles > 0 &&
+        const bool can_slab = p->use_slab && p->slabs.ok && !p->force_generic && !p->use_tiles && !p->use_planes && !p->use_sorted && p->m >= 2 &&
+                              pick_cap(std::max(p->slabs.max_t, 1)) > 0 && !(spec.solve && spec.kind == LPFNT_UPPER);
+        const bool can_tile = can_slab || can_plane || !p->force_generic && !p->use_sorted && p->use_tiles && p->m >= 2 && p->dd[1].num_tiles > 0 &&
                               pick_cap(std::max(p->max_line, p->dd[1].max_lines)) > 0;
         if (dims.size() >= 2 && dims[0] == 0 && dims[1] == 1 && can_tile) { passes.push_back({1, true}); q = 2; }
         for (; q < dims.size(); ++q) passes.push_back({dims[q], false});
@@ -824,6 +934,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         }
     }
     if ((rc = build_box(p, A, perm, hx))) return fail(rc);
+    if ((rc = build_slabs(p, hx))) return fail(rc);
     if (!hx.sorted0.empty())
         if ((rc = upload(&p->d_sorted0, reinterpret_cast<const int2 *>(hx.sorted0.data()), hx.sorted0.size(), p))) return fail(rc);
     if (!hx.eval_block.empty()) {
@@ -858,6 +969,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
     for (int h = 0; h < 3; ++h) cudaFree(p->box.d_item[h]);
+    cudaFree(p->slabs.d_desc); cudaFree(p->slabs.d_item0); cudaFree(p->slabs.d_item1);
     cudaFree(p->box.d_pline); cudaFree(p->box.d_perm16); cudaFree(p->box.d_line_off16);
     cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_sorted0); cudaFree(p->d_plane_line); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
@@ -886,6 +998,11 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_planes") == 0) { p->use_planes = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "use_slab") == 0) {
+        p->use_slab = value ? 1 : 0;
+        if (value == 2 && p->slabs.n_slabs > 0) p->slabs.ok = true;  // 2: force the slab kernel even for sparsely filled slabs (tests)
+        return LPFNT_OK;
+    }
     if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < -1 ? -1 : (value > 3 ? 3 : value); return LPFNT_OK; }
     if (std::strcmp(name, "use_two_lanes") == 0) { p->use_two_lanes = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }

@@ -178,6 +178,25 @@ cudaError_t launch_whole2<T>(int mode, bool fma, const WholeArgs &a, const doubl
     }
 }
 
+template <>
+cudaError_t launch_slab<T>(int mode, bool fma, const SlabArgs &a, const double *tri, int grid, cudaStream_t s) {
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    switch (mode) {
+        case kLowerMatvec:
+            if (fma) k_slab<T, kLowerMatvec, true><<<grid, kSlabThreads, 0, s>>>(a, M);
+            else k_slab<T, kLowerMatvec, false><<<grid, kSlabThreads, 0, s>>>(a, M);
+            break;
+        case kUpperMatvec:
+            if (fma) k_slab<T, kUpperMatvec, true><<<grid, kSlabThreads, 0, s>>>(a, M);
+            else k_slab<T, kUpperMatvec, false><<<grid, kSlabThreads, 0, s>>>(a, M);
+            break;
+        case kLowerSolve: k_slab<T, kLowerSolve, false><<<grid, kSlabThreads, 0, s>>>(a, M); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 namespace {
 template <int MODE, bool FMA>
 cudaError_t whole3_launch(const Whole3Args &a, const BoxConst &c, const PackedTri<T> &M, int grid, cudaStream_t s) {

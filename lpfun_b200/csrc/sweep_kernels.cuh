@@ -60,8 +60,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Apply the triangular operator to a register-resident fibre of length t, in place.
 // ROWS = output rows folded side by side in the lower mat-vec (independent accumulators).
+// tg: bound used by the row-block guards of the lower mat-vec.  Callers may pass the WARP maximum of t
+// (one value per warp: the guards then never diverge and the compiler does not have to keep 32 per-lane
+// predicates alive); rows beyond a lane's own t are computed on zeros and never stored.
 template <int MAXT, int MODE, bool FMA, int ROWS = 4>
-__device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M) {
+__device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M, const int tg) {
     if constexpr (MODE == kLowerMatvec) {
         // Outputs from the top down: out_k only reads x_j, j <= k, so it may overwrite x_k.
         // ROWS rows are folded side by side (independent accumulators): the sweeps are latency
@@ -71,7 +74,7 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
         static_assert(MAXT % ROWS == 0, "rows are processed in blocks of ROWS");
 #pragma unroll
         for (int k = MAXT - 1; k >= ROWS - 1; k -= ROWS) {
-            if (k - (ROWS - 1) < t) {
+            if (k - (ROWS - 1) < tg) {
                 double acc[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) acc[r] = 0.0;
@@ -135,6 +138,41 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
             }
         }
     }
+}
+
+// Lower mat-vec with the INPUT STREAMED (shared memory) and the outputs accumulated in registers:
+// step j reads x_j once and feeds it into out_j .. out_{tmax-1}.  Every out_k still receives its
+// terms in ascending j from +0.0 (bit-identical to the row form), but a thread now carries up to
+// MAXT independent chains instead of 2-4, so the 8.4-cycle DADD/DFMA latency is hidden inside ONE
+// warp; the loads of x_j overlap the arithmetic of x_{j-1}.  tmax is warp-uniform (rows beyond it
+// are skipped in blocks of four by uniform branches), t is the lane's own length (x_j = 0 beyond
+// it; rows beyond it are computed on zeros and never stored).
+template <int MAXT, bool FMA, typename LoadX>
+__device__ __forceinline__ void lower_matvec_stream(double (&acc)[MAXT], const int tmax, const PackedTri<MAXT> &M, LoadX loadx) {
+    static_assert(MAXT % 4 == 0, "rows are skipped in blocks of four");
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+        if (j < tmax) {
+            const double xj = loadx(j);
+#pragma unroll
+            for (int kb = j / 4; kb < MAXT / 4; ++kb) {
+                if (kb * 4 < tmax) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int k = kb * 4 + r;
+                        if (k >= j) acc[k] = mac<FMA>(acc[k], M.v[k * (k + 1) / 2 + j], xj);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int MAXT, int MODE, bool FMA, int ROWS = 4>
+__device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, const PackedTri<MAXT> &M) {
+    apply_fibre<MAXT, MODE, FMA, ROWS>(x, t, M, t);
 }
 
 // Two register-resident fibres swept side by side with ONE stream of matrix constants.
@@ -690,11 +728,14 @@ __global__ void __launch_bounds__(THREADS, 6) k_sweep_groups(const GroupSweepArg
         const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
         x[k] = (k < t) ? in[off + lane] : 0.0;
     }
-    apply_fibre<MAXT, MODE, FMA>(x, t, M);
+    apply_fibre<MAXT, MODE, FMA>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+    // the height is read again (L1 hit): otherwise the compiler keeps the 32 "k < t" predicates of the
+    // loads alive across the triangle code, packed into a bit mask (P2R/LOP3 chains, register pressure)
+    const int t2 = live ? int(*reinterpret_cast<const volatile uint8_t *>(a.group_t + j)) : 0;
 #pragma unroll
     for (int k = 0; k < MAXT; ++k) {
         const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
-        if (k < t) {
+        if (k < t2) {
             const int e = off + lane;
             out[a.perm_out ? a.perm_out[e] : e] = x[k];
         }
@@ -947,7 +988,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
                 __syncthreads();
                 if (tid == 0 && b + int(gridDim.x) < a.batch) issue_load(b + gridDim.x);
             }
-            apply_fibre<MAXT, MODE, FMA>(x, t, M);
+            apply_fibre<MAXT, MODE, FMA, 4>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+            // the item is read again: nothing but the fibre stays in registers across the triangle code
+            // (in particular not the 32 "k < t" predicates, which the compiler would pack into a bit mask)
+            if (tid < N1) {
+                const volatile int *vi = reinterpret_cast<const volatile int *>(sitem + h * N1 + tid);
+                const int w0 = vi[0];
+                t = int(unsigned(w0) >> 24); eo = seo + (w0 & 0xffffff); add = vi[1];
+            }
             if (last) {
                 if (a.perm_out) {
 #pragma unroll
@@ -1121,6 +1169,131 @@ k_whole3(const Whole3Args a, const __grid_constant__ PackedTri<MAXT> M, const __
                     for (int k = 0; k < MAXT; ++k)
                         if (k < t) out[int(soff[C.L[k] + a1]) + a0] = x[k];
                 }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Slab kernel (any m >= 2, any batch): coordinates 0 AND 1 in ONE pass over HBM.
+//
+// The sweeps along coordinates 0 and 1 only couple elements of the same 2-D plane
+// (a_2 .. a_{m-1} fixed).  A slab is a run of consecutive planes (<= kSlabThreads lines,
+// <= kSlabThreads element-fibres of coordinate 1, <= kSlabElems elements: contiguous in HBM).
+// One CTA works on one (function, slab) unit at a time:
+//   cp.async the slab into shared memory (fused colex gather) -> coordinate-0 sweep, thread <->
+//   line, lines in length order, in place -> barrier -> coordinate-1 sweep, thread <-> element-
+//   fibre in length order, read from shared memory into registers -> result stored from
+//   registers straight to HBM (fused colex scatter when coordinate 1 is the last one, m = 2).
+// Small footprint (<= 54 KB shared memory, 80 registers x 256 threads): three CTAs per SM run
+// unsynchronised, so the copy / barrier phases of one hide behind the arithmetic of the others --
+// the property the whole-function kernels (one CTA per SM) lack.  Units are slab-major, so the
+// CTAs running at any one time share their item tables through L2.
+// ---------------------------------------------------------------------------------------
+constexpr int kSlabThreads = 256;
+constexpr int kSlabElems = 5440;  // 43.5 KB + tables < 48 KB static shared memory
+
+struct SlabDesc {
+    int32_t e0, ne;      // first element, number of elements
+    int32_t l0, nl;      // first line, number of lines
+    int32_t c0, nc;      // first coordinate-1 item, number of them
+    int32_t pad0, pad1;
+};
+
+struct SlabArgs {
+    const double *in;
+    double *out;
+    const SlabDesc *slab;
+    const int2 *item0;        // per slab (from l0): lines, longest first: {t << 24, offset relative to the slab}
+    const int2 *item1;        // per slab (from c0): fibres, longest first: {32 + first line relative to the slab | t << 24, lane}
+    const int32_t *line_off;  // N_1 + 1
+    const int32_t *perm_in;   // colex gather (or nullptr)
+    const int32_t *perm_out;  // colex scatter (or nullptr; only when coordinate 1 is the last sweep)
+    int64_t stride;           // N
+    int32_t n_slabs, batch;
+};
+
+template <int MAXT, int MODE, bool FMA>
+__global__ void __launch_bounds__(kSlabThreads, 3) k_slab(const SlabArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+    __shared__ __align__(16) double buf[kSlabElems];
+    __shared__ int2 sitem0[kSlabThreads], sitem1[kSlabThreads];
+    __shared__ uint16_t seo[32 + kSlabThreads];
+    const int tid = threadIdx.x;
+    const int64_t units = int64_t(a.n_slabs) * a.batch;
+    int cur = -1;
+    SlabDesc d{};
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int s = int(u / a.batch), b = int(u - int64_t(s) * a.batch);
+        const double *in = a.in + int64_t(b) * a.stride;
+        double *out = a.out + int64_t(b) * a.stride;
+        __syncthreads();  // the previous unit has taken everything out of shared memory
+        if (s != cur) {
+            cur = s;
+            d = a.slab[s];
+            sitem0[tid] = tid < d.nl ? __ldg(a.item0 + d.l0 + tid) : make_int2(0, 0);
+            sitem1[tid] = tid < d.nc ? __ldg(a.item1 + d.c0 + tid) : make_int2(0, 0);
+            if (tid < 32) seo[tid] = uint16_t(tid);
+            if (tid < d.nl) seo[32 + tid] = uint16_t(__ldg(a.line_off + d.l0 + tid) - d.e0);
+        }
+        if (a.perm_in) {
+            // all gather indices first (independent loads in flight), then the copies
+            constexpr int U = (kSlabElems + kSlabThreads - 1) / kSlabThreads;
+            int src[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = tid + u * kSlabThreads;
+                src[u] = (i < d.ne) ? __ldg(a.perm_in + d.e0 + i) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (src[u] >= 0) cp_async8(buf + tid + u * kSlabThreads, in + src[u]);
+        } else {
+#pragma unroll 4
+            for (int i = tid; i < d.ne; i += kSlabThreads) cp_async8(buf + i, in + d.e0 + i);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        {   // coordinate 0
+            const int2 it = sitem0[tid];
+            const int t = int(unsigned(it.x) >> 24);
+            const double *p = buf + it.y;
+            double x[MAXT];
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? p[k] : 0.0;
+            apply_fibre<MAXT, MODE, FMA, 4>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+            // the item is read again: nothing but the fibre stays in registers across the triangle code
+            // (in particular not the 32 "k < t" predicates, which the compiler would pack into a bit mask)
+            const volatile int *vi = reinterpret_cast<volatile int *>(sitem0 + tid);
+            const int t2 = int(unsigned(vi[0]) >> 24);
+            double *q = buf + vi[1];
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k)
+                if (k < t2) q[k] = x[k];
+        }
+        __syncthreads();
+        {   // coordinate 1: element k of the fibre sits at seo[p + k] + lane
+            const int2 it = sitem1[tid];
+            const int t = int(unsigned(it.x) >> 24);
+            const uint16_t *eo = seo + (it.x & 0xffffff);
+            double x[MAXT];
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[eo[k] + it.y] : 0.0;
+            apply_fibre<MAXT, MODE, FMA, 4>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+            // read the item again: nothing but the fibre stays in registers across the triangle code
+            const volatile int *vi = reinterpret_cast<volatile int *>(sitem1 + tid);
+            const int2 it2 = make_int2(vi[0], vi[1]);
+            const int t2 = int(unsigned(it2.x) >> 24);
+            const uint16_t *eo2 = seo + (it2.x & 0xffffff);
+            double *o = out + d.e0 + it2.y;
+            if (a.perm_out) {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k)
+                    if (k < t2) out[__ldg(a.perm_out + d.e0 + it2.y + eo2[k])] = x[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k)
+                    if (k < t2) o[eo2[k]] = x[k];
             }
         }
     }

@@ -40,6 +40,9 @@ cudaError_t launch_whole(int mode, bool fma, const WholeArgs &a, const double *t
 inline size_t whole2_smem_bytes(int n_elem, int n_lines) {
     return size_t((n_elem + 1) & ~1) * sizeof(double) + 16 + size_t(3) * n_lines * sizeof(int2) + (size_t(32) + 2 * size_t(n_lines)) * sizeof(uint16_t) + 16;
 }
+// slab kernel: coordinates 0 and 1 in one pass (any m >= 2)
+template <int MAXT>
+cudaError_t launch_slab(int mode, bool fma, const SlabArgs &a, const double *tri, int grid, cudaStream_t s);
 // third generation (box layout, producer warps)
 template <int MAXT>
 cudaError_t launch_whole3(int mode, bool fma, const Whole3Args &a, const BoxConst &c, const double *tri, int grid, cudaStream_t s);

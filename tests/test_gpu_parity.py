@@ -149,14 +149,18 @@ def test_chebyshev_vs_oracle_larger(T):
         t.close()
 
 
-@pytest.mark.parametrize("whole", [2, 3])
+@pytest.mark.parametrize("whole", [2, 3, -2])
 @pytest.mark.parametrize("name", ["d3n7_cheb", "d2n8_cheb", "d2n6_inf_cheb", "d3n7_cheb_solve", "d3n6_inf", "c1_d2n10", "d3n12_p1", "d3n9_p05"])
 def test_whole_function_kernels_more_shapes(T, name, whole):
     """The one-pass whole-function kernels (bulk-copy k_whole2, box-layout k_whole3) on upper-triangular
     sweeps (Chebyshev), p = inf / 1 / 0.5 sets and m = 2; batched so that every CTA loops over several functions."""
     g = load_case(name)
     t = make(T, g, exact_ifnt=True)
-    t.set_option("use_whole", whole)
+    if whole == -2:  # the slab kernel (coordinates 0 and 1 in one pass), forced on
+        t.set_option("use_whole", 0)
+        t.set_option("use_slab", 2)
+    else:
+        t.set_option("use_whole", whole)
     reps = 40
     got = t.fnt(np.tile(g["values"], (reps, 1)))
     assert np.array_equal(got, np.tile(g["fnt"], (reps, 1)))
@@ -390,6 +394,8 @@ def test_c5_dx_eval_vs_oracle(T):
     {"use_whole": 0, "use_two_lanes": 1},
     {"use_whole": 2},
     {"use_whole": 3},
+    {"use_whole": 0, "use_slab": 2},
+    {"use_whole": 0, "use_slab": 0},
     {},
 ])
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d6n4", "d2n7_inf", "d3n12_solve", "c4_d3n30"])
