@@ -271,6 +271,17 @@ def run_ours(args):
                 "kernels": trace, "dominant_kernel": dom[0]}
     if dom[0]:
         roofline["dominant_kernel_sweep_GBs"] = 16.0 * N * B / (dom[1]["avg_ms"] * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel, per launch, from the committed `ncu --set full` capture of this
+        # very command (profiles/): only reported when kernel, N and batch match the capture
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+                tr = json.load(f)
+            if dom[0].startswith(tr["kernel"]) and tr["N"] == N and tr["batch_per_gpu"] == B:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tr["source"]
+                roofline["algorithmic_bytes_per_launch"] = 16.0 * N * B
+        except (OSError, KeyError, ValueError):
+            pass
 
     # ---------------- e2e: host (pinned) buffers through the public API ----------------
     Be = min(B, args.e2e_batch)
