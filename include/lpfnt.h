@@ -158,6 +158,9 @@ int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line
  * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4/5 row-tile sweep (5: fused with coordinate 0), 6/7 pipelined row-tile sweep (7: fused), 8 permutation, 9 sorted, 10/14/15 whole-function kernels, 11/12 eval, 13 planes) and its device time in ms.
  * Synchronises on the recorded events.  *count receives the number of records seen. */
+/* development aid: clock64 stamps of CTA 0 of the whole-function kernel, [4 functions][24 warps][16 stamps]
+ * (enable with option "timeline" = 1; see tools/timeline.py) */
+int lpfnt_plan_timeline_read(lpfnt_plan *plan, long long *out, int count);
 int lpfnt_plan_trace_read(lpfnt_plan *plan, int max_records, int *labels, float *ms, int *count);
 
 /* ---- operator level: what the njit dispatchers compute ---------------------------------

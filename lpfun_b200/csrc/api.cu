@@ -98,6 +98,7 @@ struct lpfnt_plan {
         int2 *d_item0 = nullptr, *d_item1 = nullptr;
     } slabs;
     int use_slab = 1;
+    long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole2 (option "timeline")
     // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
     struct Box {
         bool ok = false;
@@ -587,7 +588,7 @@ bool whole2_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int
     if (p->N >= 65536 || (p->N & 1) || p->N1 > kWhole2Threads || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
     if (reinterpret_cast<uintptr_t>(in) & 15) return false;
     for (int h = 1; h < p->m; ++h) if (!p->dd[h].sorted || !p->dd[h].ent_off16 || p->dd[h].num_sorted != p->N1) return false;
-    return whole2_smem_bytes(int(p->N), int(p->N1)) <= size_t(227) * 1024;
+    return whole2_smem_bytes(int(p->N), int(p->N1), p->has_perm) <= size_t(227) * 1024;
 }
 
 bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims) {
@@ -614,6 +615,7 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     a.perm_in = gather ? p->d_perm : nullptr;
     a.perm_out = scatter ? p->d_perm : nullptr;
     a.n_elem = int(p->N); a.n_lines = int(p->N1); a.m = p->m;
+    a.dbg = gen2 ? p->d_timeline : nullptr;
     const size_t smem = whole_smem_bytes(int(p->N), int(p->N1));
     const int threads = spec.fma ? 256 : 384;
     int occ = int(std::min<size_t>((size_t(227) * 1024) / (smem + 1024), size_t(2048 / threads)));
@@ -969,6 +971,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
     for (int h = 0; h < 3; ++h) cudaFree(p->box.d_item[h]);
+    cudaFree(p->d_timeline);
     cudaFree(p->slabs.d_desc); cudaFree(p->slabs.d_item0); cudaFree(p->slabs.d_item1);
     cudaFree(p->box.d_pline); cudaFree(p->box.d_perm16); cudaFree(p->box.d_line_off16);
     cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_sorted0); cudaFree(p->d_plane_line); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
@@ -998,6 +1001,13 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_planes") == 0) { p->use_planes = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "timeline") == 0) {
+        if (value && !p->d_timeline) {
+            CK(cudaMalloc(reinterpret_cast<void **>(&p->d_timeline), 4 * 24 * 16 * sizeof(long long)));
+            CK(cudaMemset(p->d_timeline, 0, 4 * 24 * 16 * sizeof(long long)));
+        } else if (!value && p->d_timeline) { cudaFree(p->d_timeline); p->d_timeline = nullptr; }
+        return LPFNT_OK;
+    }
     if (std::strcmp(name, "use_slab") == 0) {
         p->use_slab = value ? 1 : 0;
         if (value == 2 && p->slabs.n_slabs > 0) p->slabs.ok = true;  // 2: force the slab kernel even for sparsely filled slabs (tests)
@@ -1013,6 +1023,14 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "l2_chunk_bytes") == 0) { p->l2_chunk_bytes = value; return LPFNT_OK; }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;
+}
+
+int lpfnt_plan_timeline_read(lpfnt_plan *p, long long *out, int count) {
+    if (!p || !out || !p->d_timeline) { set_error("timeline: not enabled"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, p->d_timeline, sizeof(long long) * size_t(std::min(count, 4 * 24 * 16)), cudaMemcpyDeviceToHost));
+    return LPFNT_OK;
 }
 
 int lpfnt_plan_trace_read(lpfnt_plan *p, int max_records, int *labels, float *ms, int *count) {

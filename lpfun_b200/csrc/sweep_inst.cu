@@ -154,7 +154,7 @@ namespace {
 template <int MODE, bool FMA>
 cudaError_t whole2_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, cudaStream_t s) {
     auto kern = k_whole2<T, MODE, FMA, kWhole2Threads>;
-    const size_t smem = whole2_smem_bytes(a.n_elem, a.n_lines);
+    const size_t smem = whole2_smem_bytes(a.n_elem, a.n_lines, a.perm_in || a.perm_out);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -769,6 +769,7 @@ struct WholeArgs {
     int32_t n_lines;           // N_1 = items per coordinate
     int32_t m;                 // 1..3
     int32_t batch;
+    long long *dbg;            // development: clock64 stamps of CTA 0 (k_whole2; nullptr in production)
 };
 
 template <int MAXT, int MODE, bool FMA, int ITEMS, int THREADS>
@@ -918,6 +919,13 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
                  "l"(gsrc), "r"(bytes), "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar)))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_src))), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int kWhole2Threads = 768;
@@ -932,7 +940,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
     uint64_t *bar = reinterpret_cast<uint64_t *>(buf + Npad);              // one mbarrier
     int2 *sitem = reinterpret_cast<int2 *>(bar + 2);                       // [m][N1]: {eo index | t << 24, element offset added}
     uint16_t *seo = reinterpret_cast<uint16_t *>(sitem + 3 * N1);          // [32 identity][N1 coordinate 1][N1 coordinate 2]
+    uint16_t *sperm = seo + ((32 + 2 * N1 + 7) & ~7);                      // [N] colex permutation (N < 65536), if any
     const int tid = threadIdx.x;
+    {   // the permutation is looked up once per element and function: from shared memory (30-cycle latency) instead of
+        // L1/L2 (measured: the dependent global look-ups made the scatter stores 37 % of an ifnt function's period)
+        const int32_t *pg = a.perm_in ? a.perm_in : a.perm_out;
+        if (pg)
+            for (int e = tid; e < N; e += THREADS) sperm[e] = static_cast<uint16_t>(__ldg(pg + e));
+    }
 
     // One addressing form for every coordinate: element k of an item sits at seo[p + k] + add (see k_whole).
     if (tid < 32) seo[tid] = static_cast<uint16_t>(tid);
@@ -963,21 +978,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
     if (tid == 0 && int(blockIdx.x) < a.batch) issue_load(blockIdx.x);
     unsigned parity = 0;
 
-    for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    // Item slot of this thread: the chunks of 32 items (longest first) are dealt to the warps in SNAKE order over
+    // the four SM sub-partitions (warp w runs on sub-partition w % 4): 0 1 2 3 / 3 2 1 0 / ...  With the plain
+    // order sub-partition 0 would get the longest chunk of every round (13 % more FP64 work than the average).
+    const int slot = ((tid >> 7) * 4 + (((tid >> 7) & 1) ? 3 - ((tid >> 5) & 3) : ((tid >> 5) & 3))) * 32 + (tid & 31);
+    // development timeline: [function 0..3][warp][stamp 0..15] clock64 values of CTA 0
+    int fn = 0;
+    auto stamp = [&](int id) {
+        if (a.dbg && blockIdx.x == 0 && fn < 4 && (tid & 31) == 0) {
+            long long c;
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory");
+            a.dbg[(fn * (THREADS / 32) + (tid >> 5)) * 16 + id] = c;
+        }
+    };
+    for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++fn) {
         double *out = a.out + int64_t(b) * N;
+        stamp(0);
         mbar_wait(bar, parity);
         parity ^= 1;
+        stamp(1);
 #pragma unroll 1
         for (int h = 0; h < m; ++h) {
             int t = 0, add = 0;
             const uint16_t *eo = seo;
-            if (tid < N1) { const int2 it = sitem[h * N1 + tid]; t = int(unsigned(it.x) >> 24); eo = seo + (it.x & 0xffffff); add = it.y; }
+            if (slot < N1) { const int2 it = sitem[h * N1 + slot]; t = int(unsigned(it.x) >> 24); eo = seo + (it.x & 0xffffff); add = it.y; }
             const bool last = (h == m - 1);
             double x[MAXT];
             if (h == 0 && a.perm_in) {
 #pragma unroll
-                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[__ldg(a.perm_in + add + k)] : 0.0;
+                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[sperm[add + k]] : 0.0;
                 __syncthreads();  // the gather reads other lines' slots: nobody writes before everybody has read
+            } else if (h == 0) {
+                // coordinate 0: the line is contiguous, no offset look-ups
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[add + k] : 0.0;
             } else {
 #pragma unroll
                 for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[eo[k] + add] : 0.0;
@@ -988,11 +1022,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
                 __syncthreads();
                 if (tid == 0 && b + int(gridDim.x) < a.batch) issue_load(b + gridDim.x);
             }
+            stamp(2 + 4 * h);  // loads issued (and, where a barrier follows them, complete)
             apply_fibre<MAXT, MODE, FMA, 4>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+            stamp(3 + 4 * h);  // triangle code issued
             // the item is read again: nothing but the fibre stays in registers across the triangle code
             // (in particular not the 32 "k < t" predicates, which the compiler would pack into a bit mask)
-            if (tid < N1) {
-                const volatile int *vi = reinterpret_cast<const volatile int *>(sitem + h * N1 + tid);
+            if (slot < N1) {
+                const volatile int *vi = reinterpret_cast<const volatile int *>(sitem + h * N1 + slot);
                 const int w0 = vi[0];
                 t = int(unsigned(w0) >> 24); eo = seo + (w0 & 0xffffff); add = vi[1];
             }
@@ -1000,17 +1036,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
                 if (a.perm_out) {
 #pragma unroll
                     for (int k = 0; k < MAXT; ++k)
-                        if (k < t) out[__ldg(a.perm_out + eo[k] + add)] = x[k];
+                        if (k < t) out[sperm[eo[k] + add]] = x[k];
                 } else {
 #pragma unroll
                     for (int k = 0; k < MAXT; ++k)
                         if (k < t) out[eo[k] + add] = x[k];
                 }
+                stamp(4 + 4 * h);  // stores issued
             } else {
+                if (h == 0) {
 #pragma unroll
-                for (int k = 0; k < MAXT; ++k)
-                    if (k < t) buf[eo[k] + add] = x[k];
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) buf[add + k] = x[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < MAXT; ++k)
+                        if (k < t) buf[eo[k] + add] = x[k];
+                }
+                stamp(4 + 4 * h);  // stores issued
                 __syncthreads();
+                stamp(5 + 4 * h);  // barrier passed
             }
         }
     }
