@@ -153,11 +153,18 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          slabs of planes, any m >= 2: 1 = when the slabs fill the CTA (default), 0 = off, 2 = always), "use_planes" (1 = coordinates
  *          0 and 1 fused, one warp per plane), "use_two_lanes" (1 = two adjacent lanes per thread),
  *          "eval_block" (0 = non-staged eval kernel), "debug_skip" (development: skip the arithmetic),
+ *          "host_chunk_bytes" (host-pointer calls: bytes per pipelined chunk, 0 = automatic),
  *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line
  * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4/5 row-tile sweep (5: fused with coordinate 0), 6/7 pipelined row-tile sweep (7: fused), 8 permutation, 9 sorted, 10/14/15 whole-function kernels, 11/12 eval, 13 planes) and its device time in ms.
  * Synchronises on the recorded events.  *count receives the number of records seen. */
+/* Coarse <-> fine coefficient transfer through the index map of lpfnt_ordinal_embedding / Transform.embed
+ * (src/lpfun/transform.py:850-899; README "adaptivity": fine[phi] = coarse).  restrict_ = 0: prolongation,
+ * out (batch, n_big) = 0 except out[b][phi[e]] = in[b][e]; restrict_ = 1: out (batch, n_small), out[b][e] = in[b][phi[e]].
+ * phi is a host array of n_small int64.  Synchronises `stream` before returning. */
+int lpfnt_embed_apply(int device, const int64_t *phi, int64_t n_small, int64_t n_big, const double *in, double *out, int64_t batch,
+                      int restrict_, int on_device, void *stream);
 /* development aid: clock64 stamps of CTA 0 of the whole-function kernel, [4 functions][24 warps][16 stamps]
  * (enable with option "timeline" = 1; see tools/timeline.py) */
 int lpfnt_plan_timeline_read(lpfnt_plan *plan, long long *out, int count);

@@ -98,6 +98,7 @@ struct lpfnt_plan {
         int2 *d_item0 = nullptr, *d_item1 = nullptr;
     } slabs;
     int use_slab = 1;
+    int64_t host_chunk_bytes = 0;            // host-pointer calls: bytes per pipelined chunk (H2D | sweeps | D2H on two lanes); 0 = automatic
     long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole2 (option "timeline")
     // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
     struct Box {
@@ -771,7 +772,11 @@ int run_any(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vecto
     // buffers, so that the H2D copy of chunk i+1 overlaps the sweeps and the D2H copy of chunk i
     // (PCIe is full duplex; the copies dominate this path by an order of magnitude).
     const size_t fbytes = size_t(p->N) * sizeof(double);
-    int64_t chunk = std::max<int64_t>(1, int64_t((size_t(64) << 20) / fbytes));
+    // measured on B200 / PCIe Gen5 (tools/e2e.py): 16 MB chunks are best for a 125 MB batch (5.0 vs 4.3 GDOF/s with
+    // 64 MB), 32 MB for 500 MB; below 8 MB the per-chunk launch and copy overheads take over
+    const size_t cbytes = p->host_chunk_bytes > 0 ? size_t(p->host_chunk_bytes)
+                                                  : std::min<size_t>(size_t(32) << 20, std::max<size_t>(size_t(16) << 20, size_t(batch) * fbytes / 8));
+    int64_t chunk = std::max<int64_t>(1, int64_t(cbytes / fbytes));
     if (batch < 2 * chunk) chunk = std::max<int64_t>(1, (batch + 1) / 2);
     const int lanes = batch > chunk ? 2 : 1;
     for (int l = 0; l < lanes; ++l) {
@@ -1001,6 +1006,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_planes") == 0) { p->use_planes = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "host_chunk_bytes") == 0) { p->host_chunk_bytes = value <= 0 ? 0 : std::max<int64_t>(value, 1 << 16); return LPFNT_OK; }
     if (std::strcmp(name, "timeline") == 0) {
         if (value && !p->d_timeline) {
             CK(cudaMalloc(reinterpret_cast<void **>(&p->d_timeline), 4 * 24 * 16 * sizeof(long long)));
@@ -1023,6 +1029,39 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "l2_chunk_bytes") == 0) { p->l2_chunk_bytes = value; return LPFNT_OK; }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;
+}
+
+int lpfnt_embed_apply(int device, const int64_t *phi, int64_t n_small, int64_t n_big, const double *in, double *out, int64_t batch,
+                      int restrict_, int on_device, void *stream) {
+    if (!phi || !in || !out || n_small < 1 || n_big < n_small || batch < 1) { set_error("embed_apply: bad arguments"); return LPFNT_EINVAL; }
+    for (int64_t e = 0; e < n_small; ++e)
+        if (phi[e] < 0 || phi[e] >= n_big) { set_error("embed_apply: phi is not an index map into the fine space"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t n_in = restrict_ ? n_big : n_small, n_out = restrict_ ? n_small : n_big;
+    int64_t *d_phi = nullptr;
+    double *d_in = nullptr, *d_out = nullptr;
+    int rc = LPFNT_OK;
+    auto cleanup = [&]() { cudaFree(d_phi); if (!on_device) { cudaFree(d_in); cudaFree(d_out); } };
+#define CKE(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(e__)); cleanup(); return LPFNT_ECUDA; } } while (0)
+    CKE(cudaMalloc(reinterpret_cast<void **>(&d_phi), sizeof(int64_t) * size_t(n_small)));
+    CKE(cudaMemcpyAsync(d_phi, phi, sizeof(int64_t) * size_t(n_small), cudaMemcpyHostToDevice, s));
+    if (on_device) { d_in = const_cast<double *>(in); d_out = out; }
+    else {
+        CKE(cudaMalloc(reinterpret_cast<void **>(&d_in), sizeof(double) * size_t(n_in * batch)));
+        CKE(cudaMalloc(reinterpret_cast<void **>(&d_out), sizeof(double) * size_t(n_out * batch)));
+        CKE(cudaMemcpyAsync(d_in, in, sizeof(double) * size_t(n_in * batch), cudaMemcpyHostToDevice, s));
+    }
+    if (!restrict_) CKE(cudaMemsetAsync(d_out, 0, sizeof(double) * size_t(n_out * batch), s));
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = int(std::min<int64_t>(65535, batch - b0));
+        CKE(launch_embed(d_in + b0 * n_in, d_out + b0 * n_out, d_phi, n_small, n_big, nb, restrict_ != 0, s));
+    }
+    if (!on_device) CKE(cudaMemcpyAsync(out, d_out, sizeof(double) * size_t(n_out * batch), cudaMemcpyDeviceToHost, s));
+    CKE(cudaStreamSynchronize(s));  // phi (and the staging buffers) are freed below
+#undef CKE
+    cleanup();
+    return rc;
 }
 
 int lpfnt_plan_timeline_read(lpfnt_plan *p, long long *out, int count) {

@@ -288,6 +288,12 @@ cudaError_t launch_fibre_sweep<T>(int mode, bool fma, const FibreSweepArgs &a, c
 }
 
 #if LPFNT_MAXT == 8
+cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int batch, bool restrict_, cudaStream_t s) {
+    dim3 grid(unsigned((n_small + 255) / 256), batch);
+    k_embed<<<grid, 256, 0, s>>>(in, out, phi, n_small, n_big, restrict_ ? 1 : 0);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s) {
     dim3 grid(unsigned((n + 255) / 256), batch);
     k_permute<<<grid, 256, 0, s>>>(x, y, perm, n, stride, scatter ? 1 : 0);

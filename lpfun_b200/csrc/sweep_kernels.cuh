@@ -626,6 +626,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_tiles_pipe(const PipeArgs a, con
 // runs on an L2-resident chunk): gather y[e] = x[perm[e]]  /  scatter y[perm[e]] = x[e].
 __global__ void __launch_bounds__(256) k_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int scatter);
 
+// Coarse <-> fine coefficient transfer through an ordinal embedding phi (Transform.embed, src/lpfun/transform.py:850-899,
+// README "adaptivity" workflow): prolong fine[b][phi[e]] = coarse[b][e] (fine zero-filled before), restrict
+// coarse[b][e] = fine[b][phi[e]].  Grid: (ceil(n_small / 256), batch).
+__global__ void __launch_bounds__(256) k_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int restrict_);
+
 // ---------------------------------------------------------------------------------------
 // Length-sorted sweep straight from global memory: thread j owns the j-th LONGEST element-fibre
 // of coordinate h (h = 0: the j-th longest line).  No shared memory, no barriers: the 32 lanes of
@@ -1529,6 +1534,14 @@ __global__ void __launch_bounds__(256) k_permute(const double *x, double *y, con
     const int64_t q = perm[e];
     if (scatter) yf[q] = xf[e];
     else yf[e] = xf[q];
+}
+
+__global__ void __launch_bounds__(256) k_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int restrict_) {
+    const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n_small) return;
+    const int64_t q = phi[e];
+    if (restrict_) out[int64_t(blockIdx.y) * n_small + e] = in[int64_t(blockIdx.y) * n_big + q];
+    else out[int64_t(blockIdx.y) * n_big + q] = in[int64_t(blockIdx.y) * n_small + e];
 }
 
 __global__ void __launch_bounds__(128) k_sweep_generic(const GenericArgs a) {

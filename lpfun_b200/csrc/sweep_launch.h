@@ -54,6 +54,7 @@ template <int MAXT>
 cudaError_t launch_plane_sweep(int mode, bool fma, const PlaneSweepArgs &a, const double *tri, int batch, cudaStream_t s);
 
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
+cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int batch, bool restrict_, cudaStream_t s);
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s);
 
 }  // namespace lpfnt

@@ -366,6 +366,25 @@ class Transform:
             raise ValueError("The index set of the transform `t` must already contain the index set of `self` for embedding.")
         return lpset.ordinal_embedding(self._A, t.multi_index_set)
 
+    def _transfer(self, coefficients, t: "Transform", restrict: bool):
+        phi = np.ascontiguousarray(self.embed(t), dtype=np.int64)
+        src = t if restrict else self
+        x, dev, sq = src._vec_in(coefficients, "restrict" if restrict else "prolong")
+        n_out = self._N_0 if restrict else len(t)
+        out = torch.empty((x.shape[0], n_out), dtype=torch.float64, device=x.device) if dev else np.empty((x.shape[0], n_out))
+        nat.check(nat.lib().lpfnt_embed_apply(self._device, phi.ctypes.data, self._N_0, len(t), self._ptr(x), self._ptr(out), x.shape[0],
+                                              int(restrict), int(dev), self._stream(dev)))
+        return out[0] if sq else out
+
+    def prolong(self, coefficients, t: "Transform"):
+        """Coefficients of this (coarser) space as coefficients of ``t`` (zero elsewhere): ``fine[self.embed(t)] = coarse``,
+        the adaptivity workflow of the reference's README, on the device.  Extension (the reference stops at ``embed``)."""
+        return self._transfer(coefficients, t, False)
+
+    def restrict(self, coefficients_fine, t: "Transform"):
+        """Inverse of :meth:`prolong`: the entries of a coefficient vector of ``t`` that belong to this space."""
+        return self._transfer(coefficients_fine, t, True)
+
     def __len__(self) -> int:
         return self._N_0
 

@@ -414,3 +414,30 @@ def test_alternative_kernel_families(T, name, opts):
         assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
     assert np.array_equal(t.dxT(g["rnd"], m - 1, 1), g[f"dxT_{m-1}_1"])
     t.close()
+
+
+def test_prolong_restrict_through_embed(T):
+    """Device coefficient transfer through Transform.embed (transform.py:850-899): the prolonged coefficients
+    describe the same polynomial, restrict undoes prolong, host and device paths agree."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    for m, n_c, n_f, p_c, p_f in ((2, 6, 9, 2.0, 2.0), (3, 5, 8, 1.0, 2.0), (4, 3, 5, 2.0, np.inf)):
+        from lpfun_b200.utils import leja_nodes
+
+        tc = T(m, n_c, lp_degree=p_c, report=False, nodes=leja_nodes)
+        tf = T(m, n_f, lp_degree=p_f, report=False, nodes=leja_nodes)
+        phi = tc.embed(tf)
+        c = rng.standard_normal((3, len(tc)))
+        f = tc.prolong(c, tf)
+        want = np.zeros((3, len(tf)))
+        want[:, phi] = c
+        assert np.array_equal(f, want)
+        assert np.array_equal(tc.restrict(f, tf), c)
+        fd = tc.prolong(torch.as_tensor(c[0], device="cuda"), tf)
+        assert fd.is_cuda and np.array_equal(fd.cpu().numpy(), want[0])
+        pts = rng.uniform(-1, 1, (64, m))
+        assert relmax(tf.eval(f[0], pts), tc.eval(c[0], pts)) <= 1e-11
+        with pytest.raises(ValueError):
+            tf.prolong(f, tc)
+        tc.close(); tf.close()
