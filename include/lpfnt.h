@@ -184,6 +184,12 @@ int lpfnt_plan_trace_read(lpfnt_plan *plan, int max_records, int *labels, float 
 int lpfnt_itransform(lpfnt_plan *plan, const double *packed, int kind, int arith,
                      const double *in, double *out, int64_t batch, int gather_perm,
                      int scatter_perm, int on_device, void *stream);
+/* The same triangular operator (mat-vec, or solve when solve != 0) along the coordinates selected by dims_mask
+ * (bit h = coordinate h), in ascending order, in internal (A) order without permutation.  This is the building
+ * block of the sharded single transform (lpfun_b200/sharding.py): coordinates 0..m-2 on a slab of planes,
+ * the last coordinate on re-distributed columns. */
+int lpfnt_sweep(lpfnt_plan *plan, const double *packed, int kind, int solve, int arith, uint32_t dims_mask,
+                const double *in, double *out, int64_t batch, int on_device, void *stream);
 int lpfnt_transform(lpfnt_plan *plan, const double *packed, int kind, const double *in,
                     double *out, int64_t batch, int gather_perm, int scatter_perm,
                     int on_device, void *stream);

@@ -44,6 +44,7 @@ def _declare(L):
     L.lpfnt_host_free.argtypes = [vp]
     L.lpfnt_plan_create.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(vp)]
     L.lpfnt_plan_set_upper_factors.argtypes = [vp, vp, vp, i32]
+    L.lpfnt_sweep.argtypes = [vp, vp, i32, i32, i32, C.c_uint32, vp, vp, i64, i32, vp]
     L.lpfnt_embed_apply.argtypes = [i32, vp, i64, i64, vp, vp, i64, i32, i32, vp]
     L.lpfnt_plan_destroy.argtypes = [vp]
     L.lpfnt_plan_device_bytes.restype = i64

@@ -162,12 +162,15 @@ void trace_end(lpfnt_plan *p, cudaStream_t s) {
 // capacity cap (see PackedTri): lower stays row-major, upper becomes its transposed lower form.
 void repack(const double *src, int n1, int kind, int cap, std::vector<double> &dst) {
     dst.assign(tri_size(cap), 0.0);
+    // a sub-set of the index set (a slab of planes, sharding.py) may only have lines shorter than n1: its kernels use
+    // the leading cap x cap block (atoms.py:1241-1243)
+    const int nn = std::min(n1, cap);
     if (kind == LPFNT_LOWER) {
-        std::copy(src, src + tri_size(n1), dst.begin());
+        std::copy(src, src + tri_size(nn), dst.begin());
     } else {
-        for (int k = 0; k < n1; ++k) {
+        for (int k = 0; k < nn; ++k) {
             const double *row = src + int64_t(k) * n1 - int64_t(k) * (k - 1) / 2;
-            for (int j = k; j < n1; ++j) dst[j * (j + 1) / 2 + k] = row[j - k];
+            for (int j = k; j < nn; ++j) dst[j * (j + 1) / 2 + k] = row[j - k];
         }
     }
     // unit diagonal beyond n1 keeps the (never executed) padded solve rows finite
@@ -1098,6 +1101,17 @@ int lpfnt_itransform(lpfnt_plan *p, const double *packed, int kind, int arith, c
     if (kind != LPFNT_LOWER && kind != LPFNT_UPPER) { set_error("kind must be LPFNT_LOWER or LPFNT_UPPER"); return LPFNT_EINVAL; }
     SweepSpec spec{packed, kind, false, arith == LPFNT_ARITH_FMA};
     return run_any(p, spec, all_dims(p->m), in, out, batch, gather_perm != 0, scatter_perm != 0, on_device, stream);
+}
+
+int lpfnt_sweep(lpfnt_plan *p, const double *packed, int kind, int solve, int arith, uint32_t dims_mask, const double *in, double *out,
+                int64_t batch, int on_device, void *stream) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (kind != LPFNT_LOWER && kind != LPFNT_UPPER) { set_error("kind must be LPFNT_LOWER or LPFNT_UPPER"); return LPFNT_EINVAL; }
+    std::vector<int> dims;
+    for (int h = 0; h < p->m; ++h) if (dims_mask >> h & 1u) dims.push_back(h);
+    if (dims.empty() || (p->m < 32 && (dims_mask >> p->m) != 0)) { set_error("sweep: dims_mask selects no coordinate or one beyond m - 1"); return LPFNT_EINVAL; }
+    SweepSpec spec{packed, kind, solve != 0, solve == 0 && arith == LPFNT_ARITH_FMA};
+    return run_any(p, spec, dims, in, out, batch, false, false, on_device, stream);
 }
 
 int lpfnt_transform(lpfnt_plan *p, const double *packed, int kind, const double *in, double *out, int64_t batch,

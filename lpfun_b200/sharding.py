@@ -60,3 +60,270 @@ def sharded_apply(fn, full_rows, group=None, gather: bool = True):
     a, b = row_block(full_rows.shape[0], rank, world)
     local = fn(full_rows[a:b])
     return gather_rows(local, full_rows.shape[0], group) if gather else local
+
+
+# ---------------------------------------------------------------------------------------------
+# Sharded SINGLE transform: one coefficient vector too large (or too slow)
+# for one GPU.  The sweeps along coordinates 0..m-2 only couple elements with the same last
+# coordinate k = alpha_{m-1}, the sweep along coordinate m-1 only elements with the same
+# (alpha_0..alpha_{m-2}).  So
+#   * "slab" layout : rank r owns a run of planes k in [ks[r], ks[r+1]) -- a contiguous piece of the
+#                     internal (colex) order; shifted by ks[r] it is itself a downward-closed set,
+#   * "column" layout: rank r owns the complete fibres along coordinate m-1 of a run of base points
+#                     b in [bs[r], bs[r+1]) (base = the plane k = 0), longest column first -- as the
+#                     2-D set {(k, j) : k < height_j} again downward closed, columns = its lines,
+#   * one all-to-all (NCCL over NVLink / NVSwitch) moves a vector from one layout to the other.
+# fnt  = slab sweeps (0..m-2) -> all-to-all -> column sweep (m-1); result in column layout.
+# ifnt = all-to-all -> slab sweeps -> all-to-all -> column sweep -> all-to-all; result in slab layout.
+# The operation order per element is the single-GPU one, so the results are bit-identical to it.
+# ---------------------------------------------------------------------------------------------
+import numpy as np
+
+
+class SlabColumnLayout:
+    """Index logic of the two layouts and of the exchange between them (NumPy only, no GPU, no communication).
+
+    Every rank builds the same object from the full multi-index array A (colex order)."""
+
+    def __init__(self, A: np.ndarray, world: int):
+        from .core import set as lpset
+
+        A = np.ascontiguousarray(A, dtype=np.int64)
+        N, m = A.shape
+        if m < 2:
+            raise ValueError("a 1-D transform has a single fibre and cannot be sharded")
+        if world < 1:
+            raise ValueError("world must be >= 1")
+        self.N, self.m, self.world = N, m, world
+        k = A[:, m - 1]
+        K = int(k[-1]) + 1
+        self.K = K
+        plane = np.searchsorted(k, np.arange(K + 1))  # plane k = elements [plane[k], plane[k+1])
+        # slab partition: runs of planes with about N / world elements each
+        ks = [0]
+        for r in range(1, world):
+            ks.append(int(np.clip(np.searchsorted(plane, r * N / world), ks[-1], K)))
+        ks.append(K)
+        self.ks = np.asarray(ks)
+        self.slab_elem = plane[self.ks]  # element range of every rank's slab
+        # base index (position of (alpha_0..alpha_{m-2}) in plane 0) of every element
+        base_set = np.ascontiguousarray(A[: plane[1], : m - 1])
+        nb = len(base_set)
+        base = np.empty(N, dtype=np.int64)
+        base[: plane[1]] = np.arange(nb)
+        for q in range(1, K):
+            base[plane[q] : plane[q + 1]] = lpset.ordinal_embedding(np.ascontiguousarray(A[plane[q] : plane[q + 1], : m - 1]), base_set)
+        height = np.bincount(base, minlength=nb)
+        # column partition: runs of base points with about N / world elements each
+        cum = np.concatenate(([0], np.cumsum(height)))
+        bs = [0]
+        for r in range(1, world):
+            bs.append(int(np.clip(np.searchsorted(cum, r * N / world), bs[-1], nb)))
+        bs.append(nb)
+        self.bs = np.asarray(bs)
+        owner = np.searchsorted(self.bs, base, side="right") - 1  # column owner of every element
+        # column layout of every rank: its base points sorted by height (longest first, stable)
+        col_pos = np.empty(N, dtype=np.int64)  # position of every element inside its owner's column layout
+        self.col_heights = []
+        for r in range(world):
+            b0, b1 = self.bs[r], self.bs[r + 1]
+            h = height[b0:b1]
+            order = np.argsort(-h, kind="stable")
+            hs = h[order]
+            start_sorted = np.concatenate(([0], np.cumsum(hs)))[:-1]
+            start = np.empty(b1 - b0, dtype=np.int64)
+            start[order] = start_sorted
+            self.col_heights.append(hs)
+            sel = owner == r
+            col_pos[sel] = start[base[sel] - b0] + k[sel]
+        self.col_elems = np.asarray([int(hh.sum()) for hh in self.col_heights])
+        # exchange lists, slab -> column: sender s packs its elements by destination (stable in element order)
+        self.send_idx, self.send_counts, self.recv_pos, self.recv_counts = [], [], [], []
+        for s in range(world):
+            e0, e1 = self.slab_elem[s], self.slab_elem[s + 1]
+            dest = owner[e0:e1]
+            order = np.argsort(dest, kind="stable")
+            self.send_idx.append(order)
+            self.send_counts.append(np.bincount(dest, minlength=world))
+        for r in range(world):
+            pos, cnt = [], []
+            for s in range(world):
+                e0, e1 = self.slab_elem[s], self.slab_elem[s + 1]
+                sel = np.nonzero(owner[e0:e1] == r)[0] + e0
+                pos.append(col_pos[sel])
+                cnt.append(len(sel))
+            self.recv_pos.append(np.concatenate(pos) if pos else np.zeros(0, dtype=np.int64))
+            self.recv_counts.append(np.asarray(cnt))
+        self._A = A
+        self._plane = plane
+
+    def slab_set(self, r: int) -> np.ndarray:
+        """Multi-indices of rank r's slab, last coordinate shifted to start at 0 (downward closed, colex order)."""
+        e0, e1 = self.slab_elem[r], self.slab_elem[r + 1]
+        S = self._A[e0:e1].copy()
+        if len(S):
+            S[:, self.m - 1] -= self.ks[r]
+        return S
+
+    def column_set(self, r: int) -> np.ndarray:
+        """The 2-D set {(k, j) : k < height_j} of rank r's columns (coordinate 0 = k runs fastest)."""
+        hs = self.col_heights[r]
+        j = np.repeat(np.arange(len(hs)), hs)
+        kk = np.arange(int(hs.sum())) - np.repeat(np.concatenate(([0], np.cumsum(hs)))[:-1], hs)
+        return np.ascontiguousarray(np.stack([kk, j], axis=1).astype(np.int64))
+
+    # reference permutations for tests: full internal-order vector <-> concatenated layouts
+    def full_to_columns(self, full: np.ndarray, r: int) -> np.ndarray:
+        out = np.empty(self.col_elems[r], dtype=full.dtype)
+        off = 0
+        for s in range(self.world):
+            e0, e1 = self.slab_elem[s], self.slab_elem[s + 1]
+            loc = full[e0:e1][self.send_idx[s]]
+            before = int(self.send_counts[s][:r].sum())
+            cnt = int(self.send_counts[s][r])
+            out[self.recv_pos[r][off : off + cnt]] = loc[before : before + cnt]
+            off += cnt
+        return out
+
+
+class ShardedTransform:
+    """One transform sharded over the ranks of a process group (see the block comment above).
+
+    ``t`` is a constructed :class:`lpfun_b200.Transform` (used for its index set and 1-D matrices; build it with
+    ``colex_order=False`` -- the sharded vectors live in the internal order).  ``backend="cuda"`` runs the sweeps
+    with the library's kernels on this rank's GPU and exchanges with NCCL; a callable
+    ``backend(A_local, packed, kind, solve, fma, dims, x) -> y`` (NumPy) is used by the CPU tests with gloo.
+    """
+
+    def __init__(self, t, group=None, backend="cuda"):
+        if dist is None or not dist.is_initialized():
+            raise RuntimeError("ShardedTransform needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.t = t
+        self.m, self.n = t.spatial_dimension, t.polynomial_degree
+        self.layout = SlabColumnLayout(t.multi_index_set, self.world)
+        L = self.layout
+        self.backend = backend
+        self._slab_A = L.slab_set(self.rank)
+        self._col_A = L.column_set(self.rank)
+        self._slab_plan = self._col_plan = None
+        if backend == "cuda":
+            import ctypes as C
+
+            from . import _native as nat
+
+            self._nat, self._C = nat, C
+            self.device = torch.device("cuda", t.device)
+            self._slab_plan = self._make_plan(self._slab_A, self.m)
+            self._col_plan = self._make_plan(self._col_A, 2)
+            dev = self.device
+        else:
+            dev = torch.device("cpu")
+        self._send_idx = torch.as_tensor(L.send_idx[self.rank], device=dev)
+        self._recv_pos = torch.as_tensor(L.recv_pos[self.rank], device=dev)
+        self._send_counts = [int(c) for c in L.send_counts[self.rank]]
+        self._recv_counts = [int(c) for c in L.recv_counts[self.rank]]
+        self.exchanges = 0
+
+    # -- plans -------------------------------------------------------------------------------
+    def _make_plan(self, A, m):
+        if len(A) == 0:
+            return None
+        nat, C = self._nat, self._C
+        plan = C.c_void_p()
+        A = np.ascontiguousarray(A, dtype=np.int64)
+        nat.check(nat.lib().lpfnt_plan_create(m, self.n, len(A), A.ctypes.data, None, None, None, None, None, None, self.t.device, C.byref(plan)))
+        return plan
+
+    def close(self):
+        if self.backend == "cuda":
+            for p in (self._slab_plan, self._col_plan):
+                if p:
+                    self._nat.lib().lpfnt_plan_destroy(p)
+            self._slab_plan = self._col_plan = None
+
+    # -- local sweeps ------------------------------------------------------------------------
+    def _sweep(self, which, spec, x):
+        packed, kind, solve, fma = spec
+        if x.numel() == 0:
+            return x
+        if which == "slab":
+            A, plan, dims = self._slab_A, self._slab_plan, list(range(self.m - 1))
+        else:
+            A, plan, dims = self._col_A, self._col_plan, [0]
+        if self.backend == "cuda":
+            nat = self._nat
+            mask = 0
+            for h in dims:
+                mask |= 1 << h
+            x = x.contiguous()
+            out = torch.empty_like(x)
+            stream = self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            nat.check(nat.lib().lpfnt_sweep(plan, packed.ctypes.data, kind, int(solve), int(fma), mask, x.data_ptr(), out.data_ptr(), 1, 1, stream))
+            return out
+        return torch.as_tensor(self.backend(A, packed, kind, solve, fma, dims, x.numpy()))
+
+    # -- exchange ----------------------------------------------------------------------------
+    def _to_columns(self, slab):
+        send = slab[self._send_idx]
+        recv = torch.empty(sum(self._recv_counts), dtype=slab.dtype, device=slab.device)
+        dist.all_to_all_single(recv, send, self._recv_counts, self._send_counts, group=self.group)
+        self.exchanges += 1
+        cols = torch.empty_like(recv)
+        cols[self._recv_pos] = recv
+        return cols
+
+    def _to_slab(self, cols):
+        send = cols[self._recv_pos]
+        recv = torch.empty(sum(self._send_counts), dtype=cols.dtype, device=cols.device)
+        dist.all_to_all_single(recv, send, self._send_counts, self._recv_counts, group=self.group)
+        self.exchanges += 1
+        slab = torch.empty_like(recv)
+        slab[self._send_idx] = recv
+        return slab
+
+    # -- operator sequences (transform.py:455-551, 578-632) --------------------------------------
+    def _specs(self, op):
+        from . import _native as nat
+
+        t = self.t
+        LOWER, UPPER = nat.LPFNT_LOWER, nat.LPFNT_UPPER
+        if op == "fnt":
+            if t._Vx_ut is not None:
+                if t._inv_Vx_lt is None:
+                    raise NotImplementedError("sharded fnt of an LU-factorised basis needs precomputation=True")
+                return [(t._inv_Vx_lt, LOWER, False, False), (t._inv_Vx_ut, UPPER, False, False)]
+            if t._inv_Vx_lt is not None:
+                return [(t._inv_Vx_lt, LOWER, False, False)]
+            return [(t._Vx_lt, LOWER, True, False)]
+        fma = not t._exact_ifnt
+        if t._Vx_ut is not None:
+            return [(t._Vx_ut, UPPER, False, fma), (t._Vx_lt, LOWER, False, fma)]
+        return [(t._Vx_lt, LOWER, False, fma)]
+
+    def fnt(self, values_slab):
+        """Function values of this rank's slab (internal order) -> coefficients of this rank's columns."""
+        x, cols = values_slab, None
+        for i, spec in enumerate(self._specs("fnt")):
+            if i > 0:
+                x = self._to_slab(cols)
+            cols = self._sweep("cols", spec, self._to_columns(self._sweep("slab", spec, x)))
+        return cols
+
+    def ifnt(self, coeffs_cols):
+        """Coefficients of this rank's columns -> function values of this rank's slab (internal order)."""
+        cols = coeffs_cols
+        for spec in self._specs("ifnt"):
+            x = self._to_slab(cols)
+            cols = self._sweep("cols", spec, self._to_columns(self._sweep("slab", spec, x)))
+        return self._to_slab(cols)
+
+    # -- helpers for callers that hold the full vector ---------------------------------------
+    def slab_of(self, full):
+        e0, e1 = self.layout.slab_elem[self.rank], self.layout.slab_elem[self.rank + 1]
+        return full[e0:e1]
+
+    def columns_of(self, full):
+        """This rank's column layout of a full internal-order vector (host-side reference permutation)."""
+        return self.layout.full_to_columns(np.asarray(full), self.rank)
