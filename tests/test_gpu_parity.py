@@ -470,3 +470,45 @@ def test_sharded_single_transform_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     _run_sharded(2)
+
+
+@pytest.mark.parametrize("m,n,p", [(2, 31, 2.0), (3, 31, 2.0), (2, 32, 2.0), (2, 40, 1.0), (3, 33, 2.0), (1, 31, 2.0), (1, 45, 2.0),
+                                   (3, 30, 1.0), (3, 29, 2.0), (2, 1, 2.0), (3, 1, np.inf), (5, 2, 2.0)])
+def test_size_boundaries_vs_oracle(T, m, n, p):
+    """Capacity edges: n + 1 = 32 is the last register-resident size, above it the generic kernels take over;
+    tiny sets; odd N / N_1 (the whole-function kernel's eligibility rules)."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(100 * m + n)
+    t = T(m, n, lp_degree=p, report=False, exact_ifnt=True)
+    o = O.OracleTransform(m, n, p)
+    assert np.array_equal(t.multi_index_set, o.A) and len(t) == o.N
+    v = rng.standard_normal((3, len(t)))
+    c = t.fnt(v)
+    assert np.array_equal(c, np.stack([o.fnt(r) for r in v]))
+    assert np.array_equal(t.ifnt(c), np.stack([o.ifnt(r) for r in c]))
+    if n >= 1 and not (np.isinf(p) and m > 1):
+        assert np.array_equal(t.dx(c[0], m - 1, 1), o.dx(c[0], m - 1, 1))
+        assert np.array_equal(t.dxT(v[0], 0, 1), o.dxT(v[0], 0, 1))
+    pts = rng.uniform(-1, 1, (33, m))
+    # eval at n >= 30 mixes terms of very different size: compare to the reference-order sum with a looser bound
+    assert relmax(t.eval(c[0], pts), o.eval(c[0], pts)) <= (1e-12 if n < 25 else 1e-9)
+    t.close()
+
+
+def test_batch_beyond_the_grid_limit(T):
+    """More functions than gridDim.y allows in one launch (65 535): the launchers loop."""
+    from oracle import oracle as O
+
+    t = T(2, 4, report=False, exact_ifnt=True)
+    o = O.OracleTransform(2, 4, 2.0)
+    rng = np.random.default_rng(9)
+    B = 70001
+    v = rng.standard_normal((B, len(t)))
+    c = t.fnt(v)
+    for b in (0, 65534, 65535, 65536, B - 1):
+        assert np.array_equal(c[b], o.fnt(v[b]))
+    r = t.ifnt(c)
+    for b in (0, 65535, B - 1):
+        assert np.array_equal(r[b], o.ifnt(c[b]))
+    t.close()
