@@ -98,6 +98,14 @@ struct lpfnt_plan {
         int2 *d_item0 = nullptr, *d_item1 = nullptr;
     } slabs;
     int use_slab = 1;
+    // k_whole2 item orders per coordinate: [h][v], v = 0 sorted by length, 1 / 2 = length classes of 8 / 16 (natural order
+    // inside a class), 3 = natural; w2_order_* = variant per coordinate (2 bits each) for the exact / FMA forms.
+    // Strict length order keeps 97 % of the lanes busy but scatters a warp's lanes over many lines (shared-memory bank
+    // conflicts, 2.5-3.6x the store sectors); natural order does the opposite.  Measured at d=3, n=30, B=4096 (tools/
+    // order_sweep.py, all 64 combinations): classes of 8 for coordinates 1 and 2 are best for the exact form (0.649 vs
+    // 0.693 ms), classes of 8 / 16 for the FMA form with its scattered stores (0.473 vs 0.590 ms); coordinate 0 barely matters.
+    int2 *w2_items[3][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    int w2_order_exact = 0 | (1 << 2) | (1 << 4), w2_order_fma = 0 | (1 << 2) | (2 << 4);
     int64_t host_chunk_bytes = 0;            // host-pointer calls: bytes per pipelined chunk (H2D | sweeps | D2H on two lanes); 0 = automatic
     long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole2 (option "timeline")
     // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
@@ -406,7 +414,9 @@ int build_slabs(lpfnt_plan *p, const HostIndex &hx) {
                 max_t = std::max(max_t, t);
             }
         }
-        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return x.first > y.first; });
+        // length classes of 8, natural (plane, lane) order inside a class: a warp's lanes stay on few lines (coalesced
+        // result stores, fewer bank conflicts) at ~10 % less uniform lengths -- same trade as for k_whole2
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return (x.first + 7) / 8 > (y.first + 7) / 8; });
         for (auto &e : tmp) item1.push_back(e.second);
         desc.push_back(d);
         f = f1;
@@ -616,6 +626,11 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     a.in = src; a.out = dst;
     a.sorted[0] = p->d_sorted0; a.ent_off[0] = nullptr;
     for (int h = 1; h < p->m; ++h) { a.sorted[h] = p->dd[h].sorted; a.ent_off[h] = p->dd[h].ent_off16; }
+    if (gen2) {
+        const int ord = spec.fma ? p->w2_order_fma : p->w2_order_exact;
+        for (int h = 0; h < p->m; ++h)
+            if (p->w2_items[h][(ord >> (2 * h)) & 3]) a.sorted[h] = p->w2_items[h][(ord >> (2 * h)) & 3];
+    }
     a.perm_in = gather ? p->d_perm : nullptr;
     a.perm_out = scatter ? p->d_perm : nullptr;
     a.n_elem = int(p->N); a.n_lines = int(p->N1); a.m = p->m;
@@ -943,6 +958,38 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
             p->num_planes = D1.num_fibres;
         }
     }
+    if (m >= 2 && m <= 3 && N < 65536 && hx.max_line <= 255) {
+        for (int h = 0; h < m; ++h) {
+            std::vector<std::pair<int, int2>> nat;  // natural order with heights
+            if (h == 0) {
+                for (int64_t l = 0; l < hx.N1; ++l) {
+                    const int t = hx.line_off[l + 1] - hx.line_off[l];
+                    nat.push_back({t, make_int2(hx.line_off[l], t << 8)});
+                }
+            } else {
+                const DimTable &D = hx.dims[h];
+                if (D.max_lines > 255) continue;
+                for (int32_t f = 0; f < D.num_fibres; ++f) {
+                    const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
+                    const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
+                    for (int32_t lane = 0; lane < lanes; ++lane) {
+                        int32_t t = 0;
+                        while (t < nl && D.ent[p0 + t].len > lane) ++t;
+                        nat.push_back({t, make_int2(p0, lane | (t << 8))});
+                    }
+                }
+            }
+            const int cls[4] = {1, 8, 16, 1 << 20};
+            for (int v = 0; v < 4; ++v) {
+                std::vector<std::pair<int, int2>> s = nat;
+                const int q = cls[v];
+                std::stable_sort(s.begin(), s.end(), [q](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return (x.first + q - 1) / q > (y.first + q - 1) / q; });
+                std::vector<int2> out(s.size());
+                for (size_t i = 0; i < s.size(); ++i) out[i] = s[i].second;
+                if ((rc = upload(&p->w2_items[h][v], out.data(), out.size(), p))) return fail(rc);
+            }
+        }
+    }
     if ((rc = build_box(p, A, perm, hx))) return fail(rc);
     if ((rc = build_slabs(p, hx))) return fail(rc);
     if (!hx.sorted0.empty())
@@ -979,6 +1026,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
     for (int h = 0; h < 3; ++h) cudaFree(p->box.d_item[h]);
+    for (int h = 0; h < 3; ++h) for (int v = 0; v < 4; ++v) cudaFree(p->w2_items[h][v]);
     cudaFree(p->d_timeline);
     cudaFree(p->slabs.d_desc); cudaFree(p->slabs.d_item0); cudaFree(p->slabs.d_item1);
     cudaFree(p->box.d_pline); cudaFree(p->box.d_perm16); cudaFree(p->box.d_line_off16);
@@ -1010,6 +1058,8 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "use_planes") == 0) { p->use_planes = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "host_chunk_bytes") == 0) { p->host_chunk_bytes = value <= 0 ? 0 : std::max<int64_t>(value, 1 << 16); return LPFNT_OK; }
+    if (std::strcmp(name, "w2_order_exact") == 0) { p->w2_order_exact = int(value); return LPFNT_OK; }
+    if (std::strcmp(name, "w2_order_fma") == 0) { p->w2_order_fma = int(value); return LPFNT_OK; }
     if (std::strcmp(name, "timeline") == 0) {
         if (value && !p->d_timeline) {
             CK(cudaMalloc(reinterpret_cast<void **>(&p->d_timeline), 4 * 24 * 16 * sizeof(long long)));
