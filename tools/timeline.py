@@ -27,4 +27,8 @@ for op in ("fnt", "ifnt"):
     f = st[2]; t0 = f[:, 0].min()
     for w in (0, 1, 4, 8, 12, 16, 20, 22):
         print(f" warp {w:2d}: " + "  ".join(f"{NAMES[i]} {int(f[w, i] - t0):6d}" for i in range(13)))
+    print("   per stamp: min / max over the 23 busy warps (argmax warp):")
+    for i in range(13):
+        col = f[:23, i] - t0
+        print(f"     {NAMES[i]:16s} {int(col.min()):7d} {int(col.max()):7d}  (warp {int(col.argmax())})")
     print("   function period (top to top):", int(st[3][:, 0].min() - st[2][:, 0].min()), "cycles")
