@@ -14,6 +14,7 @@ constexpr int kEvalBlockLines = 256;  // lines per shared-memory block of the ev
 constexpr int kEvalBlockElems = 2048;  // padded doubles per block (16 KB)
 constexpr int kGroupLanes = 8;   // consecutive lanes of a fibre that stay together in k_sweep_groups
 constexpr int kLineChunk = 128;  // lines per CTA of k_sweep_lines
+constexpr int kGroupClass = 4;  // lane groups of k_sweep_groups are ordered by height class of this many rows
 constexpr int kTileRows = 256;  // lines staged in shared memory by one CTA of the tile kernels
 constexpr int kTileItems = 256; // element-fibres per CTA (two per thread, 128 threads)
 constexpr int kTileElems = 5120; // packed elements per CTA (40 KB; two data buffers + descriptor ring = 110 KB -> 2 CTAs/SM)
