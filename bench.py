@@ -412,7 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="functions per GPU")
-    ap.add_argument("--e2e-batch", type=int, default=1024)
+    ap.add_argument("--e2e-batch", type=int, default=4096)
     ap.add_argument("--eval-points", type=int, default=10_000_000)
     ap.add_argument("--skip-extras", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
