@@ -708,8 +708,9 @@ struct GroupSweepArgs {
     int32_t two_lanes;        // 1: k_sweep_groups2 (two adjacent lanes per thread)
 };
 
+// 80 registers (6 CTAs/SM) for 32-long fibres, 64 registers (8 CTAs/SM) up to 24 rows: measured -6..10 % per pass at d=6, n=20
 template <int MAXT, int MODE, bool FMA, int THREADS>
-__global__ void __launch_bounds__(THREADS, 6) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+__global__ void __launch_bounds__(THREADS, MAXT <= 24 ? 8 : 6) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     const int j = blockIdx.x * THREADS + threadIdx.x;
     const int g = j >> 3, sub = j & 7;
     const bool live = g < a.num_groups;  // whole warps stay alive for the shuffles below
