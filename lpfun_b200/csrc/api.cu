@@ -33,7 +33,7 @@ struct DeviceDim {
     uint32_t *items = nullptr, *rows0 = nullptr;
     int4 *tile_rec = nullptr;
     int2 *sorted = nullptr, *groups = nullptr;
-    uint8_t *group_t = nullptr;
+    uint8_t *group_t = nullptr, *group_cta_cap = nullptr;
     uint16_t *ent_off16 = nullptr;           // line offsets in fibre order as uint16 (whole-function kernel, N < 65536)
     int32_t num_sorted = 0, num_groups = 0;
     int2 *tile_elem = nullptr;
@@ -98,6 +98,7 @@ struct lpfnt_plan {
         int2 *d_item0 = nullptr, *d_item1 = nullptr;
     } slabs;
     int use_slab = 1;
+    int use_cta_cap = 1;                     // k_sweep_groups: per-CTA row capacity (8 / 16 / MAXT)
     // k_whole2 item orders per coordinate: [h][v], v = 0 sorted by length, 1 / 2 = length classes of 8 / 16 (natural order
     // inside a class), 3 = natural; w2_order_* = variant per coordinate (2 bits each) for the exact / FMA forms.
     // Strict length order keeps 97 % of the lanes busy but scatters a warp's lanes over many lines (shared-memory bank
@@ -294,7 +295,7 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
             if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
             const DeviceDim &d = p->dd[h];
             if (p->use_groups && d.groups) {
-                GroupSweepArgs ga{in, out, d.groups, d.group_t, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups, p->use_two_lanes};
+                GroupSweepArgs ga{in, out, d.groups, d.group_t, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups, p->use_two_lanes, p->use_cta_cap ? d.group_cta_cap : nullptr};
                 switch (cap) {
                     case 8: e = launch_group_sweep<8>(mode, spec.fma, ga, tri.data(), nb, s); break;
                     case 16: e = launch_group_sweep<16>(mode, spec.fma, ga, tri.data(), nb, s); break;
@@ -918,6 +919,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
             d.num_groups = int32_t(D.groups.size());
             if ((rc = upload(&d.groups, reinterpret_cast<const int2 *>(D.groups.data()), D.groups.size(), p))) return fail(rc);
             if ((rc = upload(&d.group_t, D.group_t.data(), D.group_t.size(), p))) return fail(rc);
+            if ((rc = upload(&d.group_cta_cap, D.group_cta_cap.data(), D.group_cta_cap.size(), p))) return fail(rc);
         }
         if (!D.tile_fib.empty()) {
             d.num_tiles = int32_t(D.tile_fib.size()) - 1;
@@ -1034,7 +1036,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     cudaFree(p->d_nodes); cudaFree(p->d_mat);
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
-        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].group_t); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
+        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].group_t); cudaFree(p->dd[h].group_cta_cap); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
     }
     for (int s = 0; s < 6; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1060,6 +1062,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "host_chunk_bytes") == 0) { p->host_chunk_bytes = value <= 0 ? 0 : std::max<int64_t>(value, 1 << 16); return LPFNT_OK; }
     if (std::strcmp(name, "w2_order_exact") == 0) { p->w2_order_exact = int(value); return LPFNT_OK; }
     if (std::strcmp(name, "w2_order_fma") == 0) { p->w2_order_fma = int(value); return LPFNT_OK; }
+    if (std::strcmp(name, "use_cta_cap") == 0) { p->use_cta_cap = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "timeline") == 0) {
         if (value && !p->d_timeline) {
             CK(cudaMalloc(reinterpret_cast<void **>(&p->d_timeline), 4 * 24 * 16 * sizeof(long long)));

@@ -50,6 +50,7 @@ struct DimTable {
     std::vector<SortedItem> sorted;      // num_threads: element-fibres, longest first
     std::vector<uint8_t> group_t;        // 8 per group: height of every lane of the run
     std::vector<SortedItem> groups;      // lane runs {first ent entry, lane0 | t << 8 | lanes << 16}, tallest first
+    std::vector<uint8_t> group_cta_cap;  // per 16 consecutive runs (one CTA of k_sweep_groups): tallest height
     std::vector<int32_t> tile_fib;       // num_tiles + 1
     std::vector<uint32_t> items;         // num_threads (indexed like the threads: thr_start[f0] + j)
     std::vector<uint32_t> rows0;         // N_1 (indexed like ent: fib_ptr[f0] + j)

@@ -706,9 +706,50 @@ struct GroupSweepArgs {
     int64_t stride;
     int32_t num_groups;
     int32_t two_lanes;        // 1: k_sweep_groups2 (two adjacent lanes per thread)
+    const uint8_t *cta_cap;   // per CTA of 128 threads (16 runs): height of its tallest fibre (or nullptr)
 };
 
-// 80 registers (6 CTAs/SM) for 32-long fibres, 64 registers (8 CTAs/SM) up to 24 rows: measured -6..10 % per pass at d=6, n=20
+// Body of k_sweep_groups for a row capacity CAP <= MAXT: the packed triangle of capacity MAXT starts with the one of
+// capacity CAP (row-major lower form), so the same kernel parameter serves every capacity.
+template <int CAP, int MAXT, int MODE, bool FMA>
+__device__ __forceinline__ void sweep_group_body(const GroupSweepArgs &a, const PackedTri<MAXT> &Mfull, const int j, const bool live,
+                                                 const int p0, const int lane, const int nl, const int sub, const int t,
+                                                 const double *in, double *out) {
+    const PackedTri<CAP> &M = reinterpret_cast<const PackedTri<CAP> &>(Mfull);
+    // The <= CAP row offsets of the run are fetched ONCE, up to four per thread (rows sub, sub+8, ...),
+    // and handed around the 8 threads of the run with shuffles: one global latency ahead of the
+    // data loads instead of a dependent descriptor load per row, and nothing to re-load for the stores
+    // (ncu: descriptor look-ups and their dependent compares were 2/3 of the issued instructions).
+    constexpr int NR = CAP / 8;
+    int offs[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) offs[i] = (sub + 8 * i < nl) ? __ldg(a.ent + p0 + sub + 8 * i).x : 0;
+    const int src_base = (threadIdx.x & 31) & ~7;
+    double x[CAP];
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
+        x[k] = (k < t) ? in[off + lane] : 0.0;
+    }
+    apply_fibre<CAP, MODE, FMA>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+    // the height is read again (L1 hit): otherwise the compiler keeps the "k < t" predicates of the
+    // loads alive across the triangle code, packed into a bit mask (P2R/LOP3 chains, register pressure)
+    const int t2 = live ? int(*reinterpret_cast<const volatile uint8_t *>(a.group_t + j)) : 0;
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) {
+        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
+        if (k < t2) {
+            const int e = off + lane;
+            out[a.perm_out ? a.perm_out[e] : e] = x[k];
+        }
+    }
+}
+
+// 80 registers (6 CTAs/SM) for 32-long fibres, 64 registers (8 CTAs/SM) up to 24 rows: measured -6..10 % per pass at d=6, n=20.
+// The runs are ordered by height, so whole CTAs late in the grid only hold short fibres: cta_cap[blockIdx.x] (host) is the
+// tallest fibre of the CTA, and the CTA runs the body unrolled for 8, 16 or MAXT rows -- in high dimensions most fibres are
+// short (d=6, n=20: 6 rows on average at a capacity of 24) and the never-taken rows' shuffle / address / predicate
+// instructions were most of the issued instructions (ncu: 70 % issue-slot utilisation).
 template <int MAXT, int MODE, bool FMA, int THREADS>
 __global__ void __launch_bounds__(THREADS, MAXT <= 24 ? 8 : 6) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     const int j = blockIdx.x * THREADS + threadIdx.x;
@@ -719,33 +760,16 @@ __global__ void __launch_bounds__(THREADS, MAXT <= 24 ? 8 : 6) k_sweep_groups(co
     const int t = live ? int(__ldg(a.group_t + j)) : 0;  // height of this lane (0: lane absent)
     const double *in = a.in + int64_t(blockIdx.y) * a.stride;
     double *out = a.out + int64_t(blockIdx.y) * a.stride;
-    // The <= MAXT row offsets of the run are fetched ONCE, four per thread (rows sub, sub+8, ...),
-    // and handed around the 8 threads of the run with shuffles: one global latency ahead of the
-    // data loads instead of a dependent descriptor load per row, and nothing to re-load for the stores
-    // (ncu: descriptor look-ups and their dependent compares were 2/3 of the issued instructions).
-    constexpr int NR = MAXT / 8;
-    int offs[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) offs[i] = (sub + 8 * i < nl) ? __ldg(a.ent + p0 + sub + 8 * i).x : 0;
-    const int src_base = (threadIdx.x & 31) & ~7;
-    double x[MAXT];
-#pragma unroll
-    for (int k = 0; k < MAXT; ++k) {
-        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
-        x[k] = (k < t) ? in[off + lane] : 0.0;
+    // (measured: helps at capacities 16 / 24 -- d=6 n=20: 34 -> 30 us per pass --, hurts by 6 % at 32, where the runs are
+    // long and the batched launches keep every SM full of tall CTAs anyway)
+    const int cap = (MAXT <= 24 && a.cta_cap) ? int(__ldg(a.cta_cap + blockIdx.x)) : MAXT;
+    if constexpr (MAXT > 8 && MAXT <= 24) {
+        if (cap <= 8) { sweep_group_body<8, MAXT, MODE, FMA>(a, M, j, live, p0, lane, nl, sub, t, in, out); return; }
     }
-    apply_fibre<MAXT, MODE, FMA>(x, t, M, __reduce_max_sync(0xffffffffu, t));
-    // the height is read again (L1 hit): otherwise the compiler keeps the 32 "k < t" predicates of the
-    // loads alive across the triangle code, packed into a bit mask (P2R/LOP3 chains, register pressure)
-    const int t2 = live ? int(*reinterpret_cast<const volatile uint8_t *>(a.group_t + j)) : 0;
-#pragma unroll
-    for (int k = 0; k < MAXT; ++k) {
-        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
-        if (k < t2) {
-            const int e = off + lane;
-            out[a.perm_out ? a.perm_out[e] : e] = x[k];
-        }
+    if constexpr (MAXT > 16 && MAXT <= 24) {
+        if (cap <= 16) { sweep_group_body<16, MAXT, MODE, FMA>(a, M, j, live, p0, lane, nl, sub, t, in, out); return; }
     }
+    sweep_group_body<MAXT, MAXT, MODE, FMA>(a, M, j, live, p0, lane, nl, sub, t, in, out);
 }
 
 // ---------------------------------------------------------------------------------------
