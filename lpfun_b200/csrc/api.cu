@@ -1259,7 +1259,9 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
     cudaStream_t s = on_device ? static_cast<cudaStream_t>(stream) : p->stream;
     const double *dc = coeffs, *dp = points;
     double *dv = values;
-    const bool fast = !p->chebyshev_eval && !p->force_generic && (p->n + 1 <= kMaxRegT) && p->m <= kEvalMaxM && p->n <= 255 && (p->m == 1 || p->d_line_alpha);
+    // the Chebyshev basis only has the block-staged fast kernel (and the generic fallback)
+    const bool fast = !p->force_generic && (p->n + 1 <= kMaxRegT) && p->m <= kEvalMaxM && p->n <= 255 && (p->m == 1 || p->d_line_alpha) &&
+                      (!p->chebyshev_eval || (p->use_eval_block && p->d_eval_block && p->d_cpad));
     const size_t cb = size_t(p->N) * sizeof(double), pb = size_t(P) * p->m * sizeof(double), vb = size_t(P) * sizeof(double);
     if (!on_device) {
         int rc = ensure_ws(p, 0, cb + pb);
@@ -1289,7 +1291,7 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
             if (blocked) {
                 EvalBlockArgs a{p->d_cpad, dp + q0 * p->m, dv + q0, p->d_eval_block, p->d_eval_line, p->d_line_alpha, np, p->num_eval_blocks, p->m};
                 trace_begin(p, 1200, s);
-                e = launch_eval_block(a, p->nodes.data(), p->n + 1, s);
+                e = launch_eval_block(a, p->nodes.data(), p->n + 1, p->chebyshev_eval != 0, s);
             } else {
                 EvalArgs a{dc, dp + q0 * p->m, dv + q0, p->d_line_off, p->d_line_alpha, np, int32_t(p->N1), p->m};
                 trace_begin(p, 300, s);

@@ -32,24 +32,31 @@ cudaError_t launch_eval_horner(const EvalArgs &a, const double *nodes, int n1, c
 }
 
 namespace {
-template <int MAXT, int PPT>
+template <int MAXT, int PPT, bool CHEB>
 cudaError_t eval_block_launch(const EvalBlockArgs &a, const double *nodes, int n1, cudaStream_t s) {
     NodeTable<MAXT> nt;
     for (int k = 0; k < MAXT; ++k) nt.v[k] = (k < n1) ? nodes[k] : 0.0;
     const int64_t per_block = int64_t(kEvalThreads) * PPT;
     const int64_t blocks = (a.num_points + per_block - 1) / per_block;
-    if (a.m <= 4) k_eval_block<MAXT, PPT, 4, kEvalThreads><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else if (a.m <= 8) k_eval_block<MAXT, PPT, 8, kEvalThreads><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else k_eval_block<MAXT, PPT, kEvalMaxM, kEvalThreads><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    if (a.m <= 4) k_eval_block<MAXT, PPT, 4, kEvalThreads, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else if (a.m <= 8) k_eval_block<MAXT, PPT, 8, kEvalThreads, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else k_eval_block<MAXT, PPT, kEvalMaxM, kEvalThreads, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
     return cudaGetLastError();
 }
 }  // namespace
 
-cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n1, cudaStream_t s) {
-    if (n1 <= 8) return eval_block_launch<8, 2>(a, nodes, n1, s);
-    if (n1 <= 16) return eval_block_launch<16, 2>(a, nodes, n1, s);
-    if (n1 <= 24) return eval_block_launch<24, 2>(a, nodes, n1, s);
-    if (n1 <= 32) return eval_block_launch<32, 1>(a, nodes, n1, s);
+cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n1, bool chebyshev, cudaStream_t s) {
+    if (chebyshev) {
+        if (n1 <= 8) return eval_block_launch<8, 2, true>(a, nodes, n1, s);
+        if (n1 <= 16) return eval_block_launch<16, 2, true>(a, nodes, n1, s);
+        if (n1 <= 24) return eval_block_launch<24, 2, true>(a, nodes, n1, s);
+        if (n1 <= 32) return eval_block_launch<32, 1, true>(a, nodes, n1, s);
+        return cudaErrorInvalidValue;
+    }
+    if (n1 <= 8) return eval_block_launch<8, 2, false>(a, nodes, n1, s);
+    if (n1 <= 16) return eval_block_launch<16, 2, false>(a, nodes, n1, s);
+    if (n1 <= 24) return eval_block_launch<24, 2, false>(a, nodes, n1, s);
+    if (n1 <= 32) return eval_block_launch<32, 1, false>(a, nodes, n1, s);
     return cudaErrorInvalidValue;
 }
 

@@ -167,7 +167,13 @@ __device__ __forceinline__ void cp_async1_e(void *smem_dst, const void *gsrc, in
     (void)bytes4;
 }
 
-template <int MAXT, int PPT, int MM, int THREADS>
+// CHEB = true evaluates in the Chebyshev basis (chebyshev2point, src/lpfun/utils.py:165-195) with the same trie walk:
+//   * coordinate 0: d0[q][k] holds T_k(x_0) (three-term recurrence, as the reference builds its basis table) and a
+//     line is the dot product sum_k c_k T_k(x_0) (the zero padding contributes nothing);
+//   * coordinates j >= 1: the lines are visited with a_j DEscending, so sum_{a_j} T_{a_j}(x_j) * below_{a_j} is a
+//     Clenshaw recurrence b = below + 2 x_j b1 - b2 with two running values per level; at a_j = 0 the level's value
+//     is b - x_j b1 and the state resets.
+template <int MAXT, int PPT, int MM, int THREADS, bool CHEB = false>
 __global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
     __shared__ __align__(16) double scb[2][kEvalCB];
     __shared__ int2 sln[2][kEvalLB];
@@ -184,8 +190,25 @@ __global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, c
             x[q][j] = (j < m) ? a.points[p * m + j] : 0.0;
             acc[q][j] = 0.0;
         }
+        if constexpr (CHEB) {
+            d0[q][0] = 1.0;
+            if (MAXT > 1) d0[q][1] = x[q][0];
 #pragma unroll
-        for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
+            for (int k = 1; k + 1 < MAXT; ++k) d0[q][k + 1] = __dsub_rn(__dmul_rn(__dmul_rn(2.0, x[q][0]), d0[q][k]), d0[q][k - 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
+        }
+    }
+    double b2[CHEB ? PPT : 1][CHEB ? MM : 1];  // Clenshaw: acc[][] holds b_{k+1}, b2[][] holds b_{k+2}
+    double res[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) res[q] = 0.0;
+    if constexpr (CHEB) {
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+#pragma unroll
+            for (int j = 0; j < MM; ++j) b2[q][j] = 0.0;
     }
 
     auto issue = [&](int bi) {  // stage block bi into buffer bi & 1
@@ -228,10 +251,17 @@ __global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, c
                     const double2 c23 = *reinterpret_cast<const double2 *>(cA + kb + 2);
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) {
-                        sA[q] = __fma_rn(sA[q], d0[q][kb + 3], c23.y);
-                        sA[q] = __fma_rn(sA[q], d0[q][kb + 2], c23.x);
-                        sA[q] = __fma_rn(sA[q], d0[q][kb + 1], c01.y);
-                        sA[q] = __fma_rn(sA[q], d0[q][kb], c01.x);
+                        if constexpr (CHEB) {
+                            sA[q] = __fma_rn(c23.y, d0[q][kb + 3], sA[q]);
+                            sA[q] = __fma_rn(c23.x, d0[q][kb + 2], sA[q]);
+                            sA[q] = __fma_rn(c01.y, d0[q][kb + 1], sA[q]);
+                            sA[q] = __fma_rn(c01.x, d0[q][kb], sA[q]);
+                        } else {
+                            sA[q] = __fma_rn(sA[q], d0[q][kb + 3], c23.y);
+                            sA[q] = __fma_rn(sA[q], d0[q][kb + 2], c23.x);
+                            sA[q] = __fma_rn(sA[q], d0[q][kb + 1], c01.y);
+                            sA[q] = __fma_rn(sA[q], d0[q][kb], c01.x);
+                        }
                     }
                 }
                 if (kb < tB) {
@@ -239,10 +269,17 @@ __global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, c
                     const double2 c23 = *reinterpret_cast<const double2 *>(cB + kb + 2);
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) {
-                        sB[q] = __fma_rn(sB[q], d0[q][kb + 3], c23.y);
-                        sB[q] = __fma_rn(sB[q], d0[q][kb + 2], c23.x);
-                        sB[q] = __fma_rn(sB[q], d0[q][kb + 1], c01.y);
-                        sB[q] = __fma_rn(sB[q], d0[q][kb], c01.x);
+                        if constexpr (CHEB) {
+                            sB[q] = __fma_rn(c23.y, d0[q][kb + 3], sB[q]);
+                            sB[q] = __fma_rn(c23.x, d0[q][kb + 2], sB[q]);
+                            sB[q] = __fma_rn(c01.y, d0[q][kb + 1], sB[q]);
+                            sB[q] = __fma_rn(c01.x, d0[q][kb], sB[q]);
+                        } else {
+                            sB[q] = __fma_rn(sB[q], d0[q][kb + 3], c23.y);
+                            sB[q] = __fma_rn(sB[q], d0[q][kb + 2], c23.x);
+                            sB[q] = __fma_rn(sB[q], d0[q][kb + 1], c01.y);
+                            sB[q] = __fma_rn(sB[q], d0[q][kb], c01.x);
+                        }
                     }
                 }
             }
@@ -252,16 +289,37 @@ __global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, c
                 if (which == 1 && li == 0) break;
                 const uint8_t *al = al_base + (li - which) * (m - 1);
                 bool carry = true;
+                double val[PPT];  // CHEB: value handed from a completed level to the next one
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) val[q] = 0.0;
 #pragma unroll
                 for (int j = 1; j < MM; ++j) {
                     if (j < m && carry) {
                         const int aj = al[j - 1];
-                        const double nd = nodes.v[aj];
+                        if constexpr (CHEB) {
+                            // Clenshaw step of level j with the completed value of level j - 1 (kept in val[q])
 #pragma unroll
-                        for (int q = 0; q < PPT; ++q) {
-                            const double below = (j == 1) ? (which == 0 ? sA[q] : sB[q]) : acc[q][j - 1];
-                            acc[q][j] = __fma_rn(acc[q][j], x[q][j] - nd, below);
-                            if (j > 1) acc[q][j - 1] = 0.0;
+                            for (int q = 0; q < PPT; ++q) {
+                                const double below = (j == 1) ? (which == 0 ? sA[q] : sB[q]) : val[q];
+                                const double b = __fma_rn(2.0 * x[q][j], acc[q][j], below - b2[q][j]);
+                                if (aj == 0) {  // level complete: its value goes up, the state resets
+                                    val[q] = __fma_rn(-x[q][j], acc[q][j], b);
+                                    if (j == m - 1) res[q] = val[q];  // the root: happens once, with the very last line
+                                    acc[q][j] = 0.0;
+                                    b2[q][j] = 0.0;
+                                } else {
+                                    b2[q][j] = acc[q][j];
+                                    acc[q][j] = b;
+                                }
+                            }
+                        } else {
+                            const double nd = nodes.v[aj];
+#pragma unroll
+                            for (int q = 0; q < PPT; ++q) {
+                                const double below = (j == 1) ? (which == 0 ? sA[q] : sB[q]) : acc[q][j - 1];
+                                acc[q][j] = __fma_rn(acc[q][j], x[q][j] - nd, below);
+                                if (j > 1) acc[q][j - 1] = 0.0;
+                            }
                         }
                         carry = (aj == 0);
                     }
@@ -279,6 +337,9 @@ __global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, c
 #pragma unroll
         for (int j = 1; j < MM; ++j)
             if (j == m - 1) v = acc[q][j];
+        if constexpr (CHEB) {
+            if (m > 1) v = res[q];
+        }
         if (p0 + q < a.num_points) a.values[p0 + q] = v;
     }
 }

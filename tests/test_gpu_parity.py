@@ -512,3 +512,22 @@ def test_batch_beyond_the_grid_limit(T):
     for b in (0, 65535, B - 1):
         assert np.array_equal(r[b], o.ifnt(c[b]))
     t.close()
+
+
+@pytest.mark.parametrize("m,n,p", [(1, 9, 2.0), (2, 12, 2.0), (3, 10, 1.0), (3, 23, 2.0), (4, 8, np.inf), (5, 6, 2.0), (3, 30, 2.0)])
+def test_chebyshev_eval_fast_kernel_vs_oracle(T, m, n, p):
+    """Block-staged Chebyshev evaluation (T_k table for coordinate 0, Clenshaw over the trie for the others) against the
+    reference-order flat sum of the oracle and against the generic fallback kernel."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(17 * m + n)
+    t = T(m, n, lp_degree=p, basis="chebyshev", report=False)
+    o = O.OracleTransform(m, n, p, basis="chebyshev")
+    c = rng.standard_normal(len(t)) / (1.0 + np.arange(len(t)))
+    pts = rng.uniform(-1, 1, (777, m))
+    want = o.eval(c, pts)
+    got = t.eval(c, pts)
+    assert relmax(got, want) <= TOL_EVAL
+    t.set_option("force_generic", 1)
+    assert relmax(t.eval(c, pts), want) <= TOL_EVAL
+    t.close()
