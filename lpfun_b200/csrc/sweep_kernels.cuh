@@ -1053,7 +1053,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
                 if (tid == 0 && b + int(gridDim.x) < a.batch) issue_load(b + gridDim.x);
             }
             stamp(2 + 4 * h);  // loads issued (and, where a barrier follows them, complete)
-            apply_fibre<MAXT, MODE, FMA, 4>(x, t, M, __reduce_max_sync(0xffffffffu, t));
+            apply_fibre<MAXT, MODE, FMA, 2>(x, t, M, __reduce_max_sync(0xffffffffu, t));
             stamp(3 + 4 * h);  // triangle code issued
             // the item is read again: nothing but the fibre stays in registers across the triangle code
             // (in particular not the 32 "k < t" predicates, which the compiler would pack into a bit mask)
