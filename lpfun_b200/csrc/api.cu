@@ -103,10 +103,11 @@ struct lpfnt_plan {
     // inside a class), 3 = natural; w2_order_* = variant per coordinate (2 bits each) for the exact / FMA forms.
     // Strict length order keeps 97 % of the lanes busy but scatters a warp's lanes over many lines (shared-memory bank
     // conflicts, 2.5-3.6x the store sectors); natural order does the opposite.  Measured at d=3, n=30, B=4096 (tools/
-    // order_sweep.py, all 64 combinations): classes of 8 for coordinates 1 and 2 are best for the exact form (0.649 vs
-    // 0.693 ms), classes of 8 / 16 for the FMA form with its scattered stores (0.473 vs 0.590 ms); coordinate 0 barely matters.
+    // order_sweep.py, all 64 combinations): classes of 16 for coordinates 1 and 2 are best for both forms (exact 0.619 vs
+    // 0.663 ms in strict order, FMA with its scattered stores 0.463 vs 0.586 ms; classes of 8 are within 0.5 %);
+    // coordinate 0 is best in strict order.
     int2 *w2_items[3][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-    int w2_order_exact = 0 | (1 << 2) | (1 << 4), w2_order_fma = 0 | (1 << 2) | (2 << 4);
+    int w2_order_exact = 0 | (2 << 2) | (2 << 4), w2_order_fma = 0 | (2 << 2) | (2 << 4);
     int64_t host_chunk_bytes = 0;            // host-pointer calls: bytes per pipelined chunk (H2D | sweeps | D2H on two lanes); 0 = automatic
     long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole2 (option "timeline")
     // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
