@@ -173,8 +173,10 @@ __device__ __forceinline__ void cp_async1_e(void *smem_dst, const void *gsrc, in
 //   * coordinates j >= 1: the lines are visited with a_j DEscending, so sum_{a_j} T_{a_j}(x_j) * below_{a_j} is a
 //     Clenshaw recurrence b = below + 2 x_j b1 - b2 with two running values per level; at a_j = 0 the level's value
 //     is b - x_j b1 and the state resets.
+// Capacity 32 (one point per thread) runs at 128 registers / 4 CTAs per SM (measured 5122 vs 4680 Gpair/s at d=3, n=30);
+// the two-point variants keep their 162 registers (forcing 128 costs them a third: 3134 vs 4707 Gpair/s at d=4, n=20).
 template <int MAXT, int PPT, int MM, int THREADS, bool CHEB = false>
-__global__ void __launch_bounds__(THREADS) k_eval_block(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
+__global__ void __launch_bounds__(THREADS, MAXT > 24 ? 4 : 1) k_eval_block(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
     __shared__ __align__(16) double scb[2][kEvalCB];
     __shared__ int2 sln[2][kEvalLB];
     __shared__ __align__(4) uint8_t sal[2][kEvalLB * (MM - 1) + 4];
