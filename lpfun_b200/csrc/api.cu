@@ -88,7 +88,7 @@ struct lpfnt_plan {
                                              // per-coordinate kernels on B200 so far, kept selectable
     int debug_skip = 0;
     int use_whole = -1;                      // whole function in shared memory, ONE pass over HBM per transform (m = 2, 3):
-                                             // -1 auto (k_whole2 when its 768 threads are at least 2/3 busy: N_1 >= 512),
+                                             // -1 auto (k_whole2 when its 768 threads are at least 2/3 busy, N_1 >= 512, and batch >= 8),
                                              // 0 off, 1 k_whole, 2 k_whole2, 3 k_whole3 (box layout, producer warp)
     // slab kernel (coordinates 0 and 1 in one pass, any m >= 2; see k_slab)
     struct Slabs {
@@ -596,8 +596,10 @@ int launch_whole3_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
 }
 
 // second-generation whole-function kernel: every sweep in one round, bulk copies need 16-byte granules
-bool whole2_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in) {
-    const bool want = p->use_whole == 2 || (p->use_whole == -1 && p->N1 >= 512);
+bool whole2_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, int64_t batch) {
+    // automatic: enough items to fill the CTA and enough functions to fill a few SMs -- a single function would run on ONE
+    // SM (measured at d=3, n=30, B=1: 29 us against 24 us for the per-coordinate kernels spread over the GPU)
+    const bool want = p->use_whole == 2 || (p->use_whole == -1 && p->N1 >= 512 && batch >= 8);
     if (!want || p->force_generic || p->m < 2 || p->m > 3 || int(dims.size()) != p->m) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
     if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
@@ -691,7 +693,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
         // in-place is safe: a function is complete in shared memory / registers before its first store
         return launch_whole3_fn(p, spec, in, out, batch, gather, scatter, s);
     }
-    if (whole2_ok(p, spec, dims, in)) {
+    if (whole2_ok(p, spec, dims, in, batch)) {
         // in-place is safe: a function is complete in shared memory / registers before its first store
         return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s, true);
     }
