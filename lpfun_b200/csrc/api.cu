@@ -603,7 +603,7 @@ bool whole2_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int
     if (!want || p->force_generic || p->m < 2 || p->m > 3 || int(dims.size()) != p->m) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
     if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
-    if (p->N >= 65536 || (p->N & 1) || p->N1 > kWhole2Threads || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
+    if (p->N >= 65536 || p->N1 > kWhole2Threads || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
     if (reinterpret_cast<uintptr_t>(in) & 15) return false;
     for (int h = 1; h < p->m; ++h) if (!p->dd[h].sorted || !p->dd[h].ent_off16 || p->dd[h].num_sorted != p->N1) return false;
     return whole2_smem_bytes(int(p->N), int(p->N1), p->has_perm) <= size_t(227) * 1024;

@@ -965,9 +965,9 @@ template <int MAXT, int MODE, bool FMA, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int N = a.n_elem, N1 = a.n_lines, m = a.m;
-    const int Npad = (N + 1) & ~1;
-    double *buf = reinterpret_cast<double *>(smem_raw);                    // [Npad]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(buf + Npad);              // one mbarrier
+    const int Npad = (N + 3) & ~1;  // N + 1 (odd N: the bulk copy moves an even number of elements) + 1 (shifted origin)
+    double *buf0 = reinterpret_cast<double *>(smem_raw);                   // [Npad], 16-byte aligned landing zone
+    uint64_t *bar = reinterpret_cast<uint64_t *>(buf0 + Npad);             // one mbarrier
     int2 *sitem = reinterpret_cast<int2 *>(bar + 2);                       // [m][N1]: {eo index | t << 24, element offset added}
     uint16_t *seo = reinterpret_cast<uint16_t *>(sitem + 3 * N1);          // [32 identity][N1 coordinate 1][N1 coordinate 2]
     uint16_t *sperm = seo + ((32 + 2 * N1 + 7) & ~7);                      // [N] colex permutation (N < 65536), if any
@@ -998,12 +998,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
     }
     __syncthreads();
 
-    const unsigned fbytes = unsigned(N) * 8u;  // multiple of 16 (host checks N even)
+    // Bulk copies move 16-byte granules between 16-byte aligned addresses.  For odd N every second function starts 8
+    // bytes off: the copy then starts one element early (mis = 1) and the function sits at buf0 + mis; an even-b function
+    // of an odd N copies one element more than it needs (the next function's first) -- except the very last function of
+    // the batch, which copies N - 1 elements and fetches its last one with an ordinary load (nothing is read past the end).
+    const bool oddN = (N & 1) != 0;
     auto issue_load = [&](int b) {
-        const char *src = reinterpret_cast<const char *>(a.in + int64_t(b) * N);
-        mbar_expect_tx(bar, fbytes);
-        for (unsigned o = 0; o < fbytes; o += kBulkPiece)
-            bulk_g2s(reinterpret_cast<char *>(buf) + o, src + o, min(kBulkPiece, fbytes - o), bar);
+        const int mis = oddN ? (b & 1) : 0;
+        const bool tail = oddN && mis == 0 && b == a.batch - 1;
+        const unsigned nbytes = unsigned(oddN ? (tail ? N - 1 : N + 1) : N) * 8u;
+        const char *src = reinterpret_cast<const char *>(a.in + int64_t(b) * N - mis);
+        mbar_expect_tx(bar, nbytes);
+        for (unsigned o = 0; o < nbytes; o += kBulkPiece)
+            bulk_g2s(reinterpret_cast<char *>(buf0) + o, src + o, min(kBulkPiece, nbytes - o), bar);
+        if (tail) buf0[N - 1] = a.in[int64_t(b) * N + N - 1];  // ordered before the consumers by the barrier after the mbarrier wait
     };
     if (tid == 0 && int(blockIdx.x) < a.batch) issue_load(blockIdx.x);
     unsigned parity = 0;
@@ -1023,9 +1031,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_whole2(const WholeArgs a, const 
     };
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x, ++fn) {
         double *out = a.out + int64_t(b) * N;
+        double *buf = buf0 + (oddN ? (b & 1) : 0);
         stamp(0);
         mbar_wait(bar, parity);
         parity ^= 1;
+        if (oddN && b == a.batch - 1) __syncthreads();  // the last function's final element came by an ordinary store of thread 0
         stamp(1);
 #pragma unroll 1
         for (int h = 0; h < m; ++h) {

@@ -38,7 +38,7 @@ template <int MAXT>
 cudaError_t launch_whole(int mode, bool fma, const WholeArgs &a, const double *tri, int grid, cudaStream_t s);
 // second generation (bulk-copy prefetch, one round per sweep, result stored from registers)
 inline size_t whole2_smem_bytes(int n_elem, int n_lines, bool perm) {
-    return size_t((n_elem + 1) & ~1) * sizeof(double) + 16 + size_t(3) * n_lines * sizeof(int2) + size_t((32 + 2 * n_lines + 7) & ~7) * sizeof(uint16_t) +
+    return size_t((n_elem + 3) & ~1) * sizeof(double) + 16 + size_t(3) * n_lines * sizeof(int2) + size_t((32 + 2 * n_lines + 7) & ~7) * sizeof(uint16_t) +
            (perm ? size_t((n_elem + 8) & ~7) * sizeof(uint16_t) : 0) + 16;
 }
 // slab kernel: coordinates 0 and 1 in one pass (any m >= 2)

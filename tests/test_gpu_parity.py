@@ -531,3 +531,23 @@ def test_chebyshev_eval_fast_kernel_vs_oracle(T, m, n, p):
     t.set_option("force_generic", 1)
     assert relmax(t.eval(c, pts), want) <= TOL_EVAL
     t.close()
+
+
+@pytest.mark.parametrize("n,B", [(25, 1), (25, 16), (28, 9), (29, 300), (12, 7)])
+def test_whole_function_kernel_odd_sizes(T, n, B):
+    """k_whole2 with an odd number of coefficients: every second function starts 8 bytes off the 16-byte grid of the bulk
+    copies (the copy starts one element early) and the last function of a batch must not read past the end."""
+    from oracle import oracle as O
+
+    t = T(3, n, report=False, exact_ifnt=True)
+    assert len(t) % 2 == 1
+    t.set_option("use_whole", 2)
+    o = O.OracleTransform(3, n, 2.0)
+    rng = np.random.default_rng(n + B)
+    v = rng.standard_normal((B, len(t)))
+    c = t.fnt(v)
+    r = t.ifnt(c)
+    for b in sorted({0, 1, B // 2, B - 2, B - 1} & set(range(B))):
+        assert np.array_equal(c[b], o.fnt(v[b])), b
+        assert np.array_equal(r[b], o.ifnt(c[b])), b
+    t.close()
