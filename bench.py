@@ -177,7 +177,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-LABEL_NAMES = {0: "k_sweep_lines", 1: "k_sweep_groups", 2: "k_sweep_generic", 3: "k_eval_horner", 4: "k_sweep_tiles", 5: "k_sweep_tiles+dim0", 6: "k_tiles_pipe", 7: "k_tiles_pipe+dim0", 8: "k_permute", 9: "k_sweep_sorted", 10: "k_whole", 11: "k_eval_pad", 12: "k_eval_block", 13: "k_sweep_planes", 14: "k_whole2", 15: "k_whole3", 16: "k_slab"}
+LABEL_NAMES = {0: "k_sweep_lines", 1: "k_sweep_groups", 2: "k_sweep_generic", 3: "k_eval_horner", 8: "k_permute", 11: "k_eval_pad", 12: "k_eval_block", 14: "k_whole", 16: "k_slab"}
 
 
 def summarize_trace(recs):

@@ -93,23 +93,24 @@ enum {
     LPFNT_TAB_THR_FIB = 4,    /* #threads: thread -> fibre                                     */
     LPFNT_TAB_LINE_ALPHA = 5, /* N_1 * (m-1) uint8 : (a_1..a_{m-1}) of every line (eval)       */
     LPFNT_TAB_LEVEL_SIZE = 6, /* m + 1 int64 : N_0, N_1, ..., 1                                */
-    LPFNT_TAB_TILE_FIB = 7,   /* tiles + 1: tile -> first fibre (a tile = consecutive fibres of h) */
-    LPFNT_TAB_TILE_ITEMS = 8, /* #threads uint32: per tile its element-fibres, longest first:
-                                 row (relative to the tile) | lane << 16 | length << 24         */
-    LPFNT_TAB_TILE_ROWS0 = 9, /* N_1 uint32: per tile its rows, longest first: row | len << 24   */
-    LPFNT_TAB_TILE_ROWPOS = 10, /* N_1 uint16: packed shared-memory offset of every row in its tile  */
-    LPFNT_TAB_TILE_ELEMROW = 11,/* N uint8: row (relative to its tile) of every packed tile element  */
-    LPFNT_TAB_TILE_ELEM = 12,   /* tiles + 1: start of each tile in the ELEMROW map (4-byte aligned)  */
-    LPFNT_TAB_TILE_NELEM = 13,  /* tiles: number of packed elements of each tile                     */
-    LPFNT_TAB_SORTED = 14,      /* 2 * #threads int32: element-fibres of coordinate h (h = 0: the lines)
-                                   longest first: {first ent entry | line offset, lane | length << 8} */
-    LPFNT_TAB_GROUPS = 15,      /* 2 * #groups int32: runs of <= 8 consecutive lanes of a fibre, tallest first:
+    LPFNT_TAB_GROUPS = 7,       /* 2 * #groups int32: runs of <= 8 consecutive lanes of a fibre, tallest first:
                                    {first ent entry, lane0 | height << 8 | lanes << 16}               */
-    LPFNT_TAB_LINE_ORDER = 16,  /* N_1 int32: lines ordered by length inside every chunk of 128 lines  */
-    LPFNT_TAB_GROUP_T = 17      /* 8 * #groups uint8: height of every lane of every lane group         */
+    LPFNT_TAB_LINE_ORDER = 8,   /* N_1 int32: lines ordered by length inside every chunk of 128 lines  */
+    LPFNT_TAB_GROUP_T = 9,      /* 8 * #groups uint8: height of every lane of every lane group         */
+    LPFNT_TAB_WHOLE_ITEMS = 10, /* uint32: item lists of the whole-function kernel, all parts and coordinates back to back in
+                                   thread order: bits 0..15 line offset (coordinate 0) / first entry in WHOLE_SEO,
+                                   bits 16..21 length, bits 22..31 lane a_0                                      */
+    LPFNT_TAB_WHOLE_SEO = 11,   /* uint16: per coordinate h >= 1 the line offsets in fibre order                */
+    LPFNT_TAB_LINE_LAST = 12    /* N_1 uint8: a_{m-1} of every line                                    */
 };
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);
+/* Item tables of the whole-function kernel (m = 2, 3; N < 65536).  lpfnt_index_whole_build re-builds them for CTAs of
+ * `threads` threads (384: two CTAs per SM, 768: one) and an item order (2 bits per coordinate, 0 strict length order,
+ * 1 / 2 classes of 8 / 16 rows, 3 natural; < 0 = default).  lpfnt_index_whole_meta fills 10 int32: ok, threads,
+ * longest item, most items of a list, {list offset, padded list length} per coordinate; returns the number written. */
+int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order);
+int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta);
 int64_t lpfnt_index_size(const lpfnt_index *index, int what, int h);
 int lpfnt_index_copy(const lpfnt_index *index, int what, int h, void *dst);
 
@@ -145,19 +146,19 @@ int64_t lpfnt_plan_device_bytes(const lpfnt_plan *plan);
 int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
 /* options: "force_generic" (1 = route every op through the unbounded-n fallback kernels),
  *          "trace" (1 = record a CUDA-event pair around every kernel launch),
- *          "use_tiles" (0 = per-coordinate line/fibre kernels instead of the row-tile kernels),
- *          "use_pipe" (1 = persistent cp.async-pipelined row-tile kernels), "use_sorted" (1 = globally
- *          length-sorted per-coordinate kernels), "use_groups" (0 = natural lane order in the fibre kernel),
  *          "use_whole" (whole function in shared memory, one pass over HBM per transform, m = 2, 3:
- *          -1 = automatic (default), 0 = off, 1/2/3 = first / bulk-copy / box-layout generation), "use_slab" (coordinates 0 and 1 in one pass over
- *          slabs of planes, any m >= 2: 1 = when the slabs fill the CTA (default), 0 = off, 2 = always), "use_planes" (1 = coordinates
- *          0 and 1 fused, one warp per plane), "use_two_lanes" (1 = two adjacent lanes per thread),
- *          "eval_block" (0 = non-staged eval kernel), "debug_skip" (development: skip the arithmetic),
- *          "host_chunk_bytes" (host-pointer calls: bytes per pipelined chunk, 0 = automatic),
- *          "l2_chunk_bytes" (batched multi-pass transforms are cut into chunks of this many bytes) */
+ *          -1 = automatic (default: batches of >= 8 functions), 0 = off, 1 = always),
+ *          "whole_threads" (-1 automatic: 384 threads and two CTAs per SM when two functions fit into shared memory,
+ *          else 768 and one; or 384 / 768), "whole_order" (item order, see lpfnt_index_whole_build),
+ *          "whole_rows" (rows of the triangle code folded side by side: 2 or 4; -1 automatic),
+ *          "use_slab" (coordinates 0 and 1 in one pass over slabs of planes, any m >= 2: 1 = when the slabs
+ *          fill the CTA (default), 0 = off, 2 = always), "use_cta_cap" (k_sweep_groups: per-CTA row capacity),
+ *          "eval_block" (0 = non-staged eval kernel), "timeline" (development: clock64 stamps of the
+ *          whole-function kernel), "host_chunk_bytes" (host-pointer calls: bytes per pipelined chunk, 0 = automatic).
+ * A plan owns one set of workspaces: use it from one host thread and one stream at a time. */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line
- * sweep, 1 fibre sweep, 2 generic sweep, 3 eval, 4/5 row-tile sweep (5: fused with coordinate 0), 6/7 pipelined row-tile sweep (7: fused), 8 permutation, 9 sorted, 10/14/15 whole-function kernels, 11/12 eval, 13 planes) and its device time in ms.
+ * sweep, 1 fibre sweep, 2 generic sweep, 3 eval (unstaged), 8 permutation, 11/12 eval (pad / block), 14 whole-function kernel, 16 slab kernel) and its device time in ms.
  * Synchronises on the recorded events.  *count receives the number of records seen. */
 /* Coarse <-> fine coefficient transfer through the index map of lpfnt_ordinal_embedding / Transform.embed
  * (src/lpfun/transform.py:850-899; README "adaptivity": fine[phi] = coarse).  restrict_ = 0: prolongation,
@@ -165,7 +166,7 @@ int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
  * phi is a host array of n_small int64.  Synchronises `stream` before returning. */
 int lpfnt_embed_apply(int device, const int64_t *phi, int64_t n_small, int64_t n_big, const double *in, double *out, int64_t batch,
                       int restrict_, int on_device, void *stream);
-/* development aid: clock64 stamps of CTA 0 of the whole-function kernel, [4 functions][24 warps][16 stamps]
+/* development aid: clock64 stamps of CTAs 0 and 1 of the whole-function kernel, [4 functions][2 CTAs][warps][16 stamps]
  * (enable with option "timeline" = 1; see tools/timeline.py) */
 int lpfnt_plan_timeline_read(lpfnt_plan *plan, long long *out, int count);
 int lpfnt_plan_trace_read(lpfnt_plan *plan, int max_records, int *labels, float *ms, int *count);

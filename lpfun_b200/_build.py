@@ -25,7 +25,6 @@ UNITS = [
     ("index_set.cpp", "index_set.o", []),
     ("api.cu", "api.o", []),
     ("eval_inst.cu", "eval_inst.o", []),
-    ("fused_inst.cu", "fused_inst.o", []),
 ] + [("sweep_inst.cu", f"sweep_T{t}.o", [f"-DLPFNT_MAXT={t}"]) for t in (8, 16, 24, 32)]
 
 
@@ -54,7 +53,7 @@ def _deps_mtime() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u[0]))]
+    units = list(UNITS)
     newest = _deps_mtime()
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB

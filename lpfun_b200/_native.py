@@ -40,6 +40,8 @@ def _declare(L):
     L.lpfnt_index_size.restype = i64
     L.lpfnt_index_size.argtypes = [vp, i32, i32]
     L.lpfnt_index_copy.argtypes = [vp, i32, i32, vp]
+    L.lpfnt_index_whole_build.argtypes = [vp, i32, i32]
+    L.lpfnt_index_whole_meta.argtypes = [vp, vp]
     L.lpfnt_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.lpfnt_host_free.argtypes = [vp]
     L.lpfnt_plan_create.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(vp)]
@@ -53,6 +55,7 @@ def _declare(L):
     L.lpfnt_plan_launch_count.argtypes = [vp]
     L.lpfnt_plan_set_option.argtypes = [vp, C.c_char_p, i64]
     L.lpfnt_plan_trace_read.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
+    L.lpfnt_plan_timeline_read.argtypes = [vp, vp, i32]
     L.lpfnt_itransform.argtypes = [vp, vp, i32, i32, vp, vp, i64, i32, i32, i32, vp]
     L.lpfnt_transform.argtypes = [vp, vp, i32, vp, vp, i64, i32, i32, i32, vp]
     L.lpfnt_dtransform.argtypes = [vp, vp, i32, i32, i32, vp, vp, i64, i32, vp]
@@ -127,9 +130,9 @@ def pinned_free(arr: np.ndarray):
 
 
 (TAB_LINE_OFF, TAB_FIB_PTR, TAB_FIB_ENT, TAB_THR_START, TAB_THR_FIB, TAB_LINE_ALPHA, TAB_LEVEL_SIZE,
- TAB_TILE_FIB, TAB_TILE_ITEMS, TAB_TILE_ROWS0, TAB_TILE_ROWPOS, TAB_TILE_ELEMROW, TAB_TILE_ELEM, TAB_TILE_NELEM, TAB_SORTED, TAB_GROUPS, TAB_LINE_ORDER, TAB_GROUP_T) = range(18)
-_TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_TILE_ITEMS: np.uint32, TAB_TILE_ROWS0: np.uint32,
-              TAB_TILE_ROWPOS: np.uint16, TAB_TILE_ELEMROW: np.uint8, TAB_GROUP_T: np.uint8}
+ TAB_GROUPS, TAB_LINE_ORDER, TAB_GROUP_T, TAB_WHOLE_ITEMS, TAB_WHOLE_SEO, TAB_LINE_LAST) = range(13)
+_TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_GROUP_T: np.uint8, TAB_WHOLE_SEO: np.uint16, TAB_LINE_LAST: np.uint8,
+              TAB_WHOLE_ITEMS: np.uint32}
 
 
 class IndexTables:
@@ -148,7 +151,19 @@ class IndexTables:
         out = np.empty(cnt, dtype=_TAB_DTYPE.get(what, np.int32))
         if cnt:
             check(lib().lpfnt_index_copy(self._h, what, h, out.ctypes.data))
-        return out.reshape(-1, 2) if what in (TAB_FIB_ENT, TAB_SORTED, TAB_GROUPS) else out
+        return out.reshape(-1, 2) if what in (TAB_FIB_ENT, TAB_GROUPS) else out
+
+    def whole_build(self, threads: int = 768, order: int = -1):
+        check(lib().lpfnt_index_whole_build(self._h, int(threads), int(order)))
+
+    def whole_meta(self) -> dict:
+        meta = np.zeros(10, dtype=np.int32)
+        lib().lpfnt_index_whole_meta(self._h, meta.ctypes.data)
+        d = dict(zip(["ok", "threads", "max_t", "max_items"], meta[:4].tolist()))
+        lists = meta[4:10].reshape(3, 2)
+        d["item_off"] = lists[:, 0].tolist()
+        d["n_items"] = lists[:, 1].tolist()
+        return d
 
     def close(self):
         if self._h:

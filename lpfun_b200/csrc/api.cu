@@ -29,23 +29,24 @@ namespace {
 struct DeviceDim {
     int32_t *thr_fib = nullptr, *thr_start = nullptr, *fib_ptr = nullptr;
     int2 *ent = nullptr;
-    int32_t *tile_fib = nullptr;
-    uint32_t *items = nullptr, *rows0 = nullptr;
-    int4 *tile_rec = nullptr;
-    int2 *sorted = nullptr, *groups = nullptr;
+    int2 *groups = nullptr;
     uint8_t *group_t = nullptr, *group_cta_cap = nullptr;
-    uint16_t *ent_off16 = nullptr;           // line offsets in fibre order as uint16 (whole-function kernel, N < 65536)
-    int32_t num_sorted = 0, num_groups = 0;
-    int2 *tile_elem = nullptr;
-    uint16_t *row_pos = nullptr;
-    int2 *row_desc = nullptr;
-    uint8_t *elem_row = nullptr;
-    int32_t num_threads = 0, max_lines = 0, num_tiles = 0;
+    int32_t num_groups = 0;
+    int32_t num_threads = 0, max_lines = 0;
 };
 
 int tri_size(int n1) { return n1 * (n1 + 1) / 2; }
 
 }  // namespace
+
+// device copy of a 1-D operator, cached per plan by content: the kernel-layout triangle for every capacity it was used
+// with (kernel parameter), and the reference-layout matrix in device memory for the generic kernel
+struct OperatorCache {
+    std::vector<double> packed;                 // reference packing, as passed by the caller
+    int kind = 0;
+    std::vector<double> tri[4];                 // kernel layout for capacity 8 / 16 / 24 / 32 (empty until needed)
+    double *d_packed = nullptr;                 // reference packing on the device (generic kernel)
+};
 
 struct lpfnt_plan {
     int device = 0;
@@ -55,12 +56,7 @@ struct lpfnt_plan {
     bool has_perm = false;
     // device tables
     int32_t *d_line_off = nullptr, *d_perm = nullptr;
-    int2 *d_sorted0 = nullptr;
     int32_t *d_line_order = nullptr;
-    int32_t *d_plane_line = nullptr;         // planes + 1: first line of every plane (level-2 node)
-    int32_t num_planes = 0;
-    int use_planes = 0;                      // coordinates 0 and 1 fused, one warp per plane (selectable; measured slower
-                                             // than the two separate passes: 0.61-0.66 ms vs 0.52 ms at d=3 n=30 B=4096)
     uint8_t *d_line_alpha = nullptr;
     int2 *d_eval_line = nullptr;
     int4 *d_eval_block = nullptr;
@@ -68,7 +64,7 @@ struct lpfnt_plan {
     int32_t num_eval_blocks = 0;
     int use_eval_block = 1;
     int64_t *d_A = nullptr;       // only for the generic eval fallback (uploaded lazily)
-    double *d_nodes = nullptr, *d_mat = nullptr;  // generic-kernel matrix scratch
+    double *d_nodes = nullptr;
     DeviceDim dd[kMaxDim + 1];
     std::vector<int64_t> hA;      // kept only when the generic eval may need it
     // host copies of the 1-D operators (reference packing)
@@ -77,6 +73,7 @@ struct lpfnt_plan {
     // T_k basis in eval (transform.py:292-302, utils.py:165-195)
     std::vector<double> Vx_ut, inv_Vx_ut;
     int chebyshev_eval = 0;
+    std::vector<OperatorCache *> ops;
     // workspaces (grown on demand): two lanes x {staged input, staged output, permutation scratch}
     double *ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -84,12 +81,18 @@ struct lpfnt_plan {
     int64_t launches = 0;
     int64_t table_bytes = 0;
     int force_generic = 0;
-    int use_tiles = 0;                       // row-tile kernels (sorted work items, fused coordinate 0); measured slower than the
-                                             // per-coordinate kernels on B200 so far, kept selectable
-    int debug_skip = 0;
-    int use_whole = -1;                      // whole function in shared memory, ONE pass over HBM per transform (m = 2, 3):
-                                             // -1 auto (k_whole2 when its 768 threads are at least 2/3 busy, N_1 >= 512, and batch >= 8),
-                                             // 0 off, 1 k_whole, 2 k_whole2, 3 k_whole3 (box layout, producer warp)
+    // whole-function kernel (m = 2, 3): tables of HostIndex::whole on the device
+    struct Whole {
+        WholeHost h;                         // host copy (items / seo dropped after the upload)
+        uint32_t *d_items = nullptr;
+        uint16_t *d_seo = nullptr, *d_perm16 = nullptr;
+        int32_t total_items = 0, seo_len = 0;
+        size_t smem_bytes = 0;
+        uint64_t attr_set = 0;               // bit per kernel instantiation: dynamic shared memory opted in on this device
+    } whole;
+    int use_whole = -1;                      // -1 auto (batches of >= 8 functions), 0 off, 1 always
+    int whole_threads = -1, whole_order = kWholeDefaultOrder, whole_rows = -1;
+    HostIndex *hx = nullptr;                 // kept for plans that can run the whole-function kernel (re-build of its tables)
     // slab kernel (coordinates 0 and 1 in one pass, any m >= 2; see k_slab)
     struct Slabs {
         bool ok = false;
@@ -99,32 +102,9 @@ struct lpfnt_plan {
     } slabs;
     int use_slab = 1;
     int use_cta_cap = 1;                     // k_sweep_groups: per-CTA row capacity (8 / 16 / MAXT)
-    // k_whole2 item orders per coordinate: [h][v], v = 0 sorted by length, 1 / 2 = length classes of 8 / 16 (natural order
-    // inside a class), 3 = natural; w2_order_* = variant per coordinate (2 bits each) for the exact / FMA forms.
-    // Strict length order keeps 97 % of the lanes busy but scatters a warp's lanes over many lines (shared-memory bank
-    // conflicts, 2.5-3.6x the store sectors); natural order does the opposite.  Measured at d=3, n=30, B=4096 (tools/
-    // order_sweep.py, all 64 combinations): classes of 16 for coordinates 1 and 2 are best for both forms (exact 0.619 vs
-    // 0.663 ms in strict order, FMA with its scattered stores 0.463 vs 0.586 ms; classes of 8 are within 0.5 %);
-    // coordinate 0 is best in strict order.
-    int2 *w2_items[3][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-    int w2_order_exact = 0 | (2 << 2) | (2 << 4), w2_order_fma = 0 | (2 << 2) | (2 << 4);
     int64_t host_chunk_bytes = 0;            // host-pointer calls: bytes per pipelined chunk (H2D | sweeps | D2H on two lanes); 0 = automatic
-    long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole2 (option "timeline")
-    // box layout of the third-generation whole-function kernel (m = 2, 3; see k_whole3)
-    struct Box {
-        bool ok = false;
-        BoxConst c{};
-        int32_t n_box = 0, n_item[3] = {0, 0, 0}, max_t = 0;
-        uint32_t *d_item[3] = {nullptr, nullptr, nullptr};
-        int2 *d_pline = nullptr;
-        uint16_t *d_perm16 = nullptr, *d_line_off16 = nullptr;
-    } box;
-    int use_two_lanes = 0;                   // two adjacent lanes per thread in the lane-group kernel
-    int use_groups = 1;                      // height-ordered lane groups in the per-coordinate fibre kernel
-    int use_sorted = 0;                      // globally length-sorted per-coordinate kernels (no shared memory)
-    int use_pipe = 0;                        // persistent cp.async-pipelined variant of the row-tile kernels
+    long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole (option "timeline")
     int num_sms = 148;
-    int64_t l2_chunk_bytes = 0;              // > 0: batched multi-pass transforms run in chunks of this many bytes (L2 reuse)
     // optional per-launch tracing (CUDA events around every kernel launch)
     int trace = 0;
     struct TraceRec { int label; cudaEvent_t a, b; };
@@ -187,6 +167,39 @@ void repack(const double *src, int n1, int kind, int cap, std::vector<double> &d
     for (int k = n1; k < cap; ++k) dst[k * (k + 1) / 2 + k] = 1.0;
 }
 
+// The operator `packed` (host, reference packing) as the plan knows it: looked up by CONTENT, so a caller may pass the
+// same matrix from any buffer; re-packing and the upload for the generic kernel happen once per plan, not per call.
+OperatorCache *find_operator(lpfnt_plan *p, const double *packed, int kind) {
+    const size_t cnt = size_t(tri_size(p->n + 1));
+    for (OperatorCache *oc : p->ops)
+        if (oc->kind == kind && std::memcmp(oc->packed.data(), packed, cnt * sizeof(double)) == 0) return oc;
+    if (p->ops.size() >= 64) {  // a caller streaming ever-changing matrices: recycle the oldest entry
+        OperatorCache *old = p->ops.front();
+        p->ops.erase(p->ops.begin());
+        if (old->d_packed) { cudaDeviceSynchronize(); cudaFree(old->d_packed); }
+        delete old;
+    }
+    OperatorCache *oc = new OperatorCache();
+    oc->packed.assign(packed, packed + cnt);
+    oc->kind = kind;
+    p->ops.push_back(oc);
+    return oc;
+}
+const double *operator_tri(lpfnt_plan *p, OperatorCache *oc, int cap) {
+    std::vector<double> &t = oc->tri[cap / 8 - 1];
+    if (t.empty()) repack(oc->packed.data(), p->n + 1, oc->kind, cap, t);
+    return t.data();
+}
+int operator_device(lpfnt_plan *p, OperatorCache *oc, const double **d) {
+    if (!oc->d_packed) {
+        CK(cudaMalloc(reinterpret_cast<void **>(&oc->d_packed), oc->packed.size() * sizeof(double)));
+        CK(cudaMemcpy(oc->d_packed, oc->packed.data(), oc->packed.size() * sizeof(double), cudaMemcpyHostToDevice));
+        p->table_bytes += int64_t(oc->packed.size() * sizeof(double));
+    }
+    *d = oc->d_packed;
+    return LPFNT_OK;
+}
+
 int pick_cap(int len) {
     if (len <= 8) return 8;
     if (len <= 16) return 16;
@@ -200,12 +213,16 @@ struct SweepSpec {
     int kind;              // LPFNT_LOWER / LPFNT_UPPER
     bool solve;
     bool fma;
+    OperatorCache *op = nullptr;  // resolved once per call (run_any)
 };
 
 int sweep_mode(const SweepSpec &s) {
     if (s.kind == LPFNT_LOWER) return s.solve ? kLowerSolve : kLowerMatvec;
     return s.solve ? kUpperSolve : kUpperMatvec;
 }
+
+#define LAUNCH_CAP(cap, call8, call16, call24, call32) \
+    switch (cap) { case 8: e = call8; break; case 16: e = call16; break; case 24: e = call24; break; default: e = call32; break; }
 
 int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s);
 
@@ -215,106 +232,46 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
     const int n1 = p->n + 1;
     int mode = sweep_mode(spec);
     if (mode == kUpperSolve && h >= 1) mode = kUpperSolveDesc;  // the reference's fold order there (atoms.py:391-402)
-    const int len = (h == 0) ? p->max_line : std::max(p->dd[h].max_lines, fuse0 ? p->max_line : 0);
-    const bool slab_ok = p->use_slab && p->slabs.ok && !p->force_generic && !p->use_tiles && !p->use_planes && !p->use_sorted &&
-                         pick_cap(std::max(p->slabs.max_t, 1)) > 0 && !(spec.solve && spec.kind == LPFNT_UPPER);
-    if (fuse0 && h == 1 && slab_ok) return launch_slab_pass(p, spec, src, dst, batch, gather, scatter, s);
-    const bool planes = fuse0 && h == 1 && p->use_planes && p->num_planes > 0;
-    const bool tiles = !planes && h >= 1 && p->use_tiles && !p->use_sorted && p->dd[h].num_tiles > 0;
-    if (fuse0 && !tiles && !planes) { set_error("internal: fused coordinate-0 sweep needs the tile kernel"); return LPFNT_EINVAL; }
-    const int cap = p->force_generic ? 0 : pick_cap(std::max(len, 1));
-    std::vector<double> tri;
-    if (cap) repack(spec.packed, n1, spec.kind, cap, tri);
-    else {
-        // generic kernel reads the matrix from device memory (stream ordered copy of a small table)
-        CK(cudaMemcpyAsync(p->d_mat, spec.packed, sizeof(double) * tri_size(n1), cudaMemcpyHostToDevice, s));
+    if (fuse0) {
+        if (h != 1) { set_error("internal: only coordinate 1 fuses with coordinate 0"); return LPFNT_EINVAL; }
+        return launch_slab_pass(p, spec, src, dst, batch, gather, scatter, s);
     }
+    const int len = (h == 0) ? p->max_line : p->dd[h].max_lines;
+    const int cap = p->force_generic ? 0 : pick_cap(std::max(len, 1));
+    if (cap && h >= 1 && !p->dd[h].groups) { set_error("internal: lane-group tables missing"); return LPFNT_EINVAL; }
+    const double *tri = cap ? operator_tri(p, spec.op, cap) : nullptr;
+    const double *d_mat = nullptr;
+    if (!cap) { int rc = operator_device(p, spec.op, &d_mat); if (rc) return rc; }
     for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
         const int nb = int(std::min<int64_t>(65535, batch - b0));
         const double *in = src + b0 * p->N;
         double *out = dst + b0 * p->N;
         cudaError_t e = cudaSuccess;
-        trace_begin(p, (cap == 0 ? 200 : (planes ? 1300 : (p->use_sorted ? 900 : (h == 0 ? 0 : (tiles ? (fuse0 ? 500 : 400) : 100))))) + h, s);
-        if (planes && cap != 0) {
-            PlaneSweepArgs pa{in, out, p->d_line_off, p->d_plane_line, gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, p->num_planes};
-            switch (cap) {
-                case 8: e = launch_plane_sweep<8>(mode, spec.fma, pa, tri.data(), nb, s); break;
-                case 16: e = launch_plane_sweep<16>(mode, spec.fma, pa, tri.data(), nb, s); break;
-                case 24: e = launch_plane_sweep<24>(mode, spec.fma, pa, tri.data(), nb, s); break;
-                default: e = launch_plane_sweep<32>(mode, spec.fma, pa, tri.data(), nb, s); break;
-            }
-            trace_end(p, s);
-            p->launches += 1;
-            if (e != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
-            continue;
-        }
-        const bool sorted_ok = cap != 0 && p->use_sorted && !fuse0 && (h == 0 ? p->d_sorted0 != nullptr : p->dd[h].sorted != nullptr);
-        if (sorted_ok) {
-            const int nit = (h == 0) ? int(p->N1) : p->dd[h].num_sorted;
-            SortedSweepArgs a{in, out, h == 0 ? p->d_sorted0 : p->dd[h].sorted, h == 0 ? nullptr : p->dd[h].ent,
-                              gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, nit};
-            // batched: one CTA per function when it fits, so that the L1 keeps the function resident
-            const int threads = (batch > 1 && nit <= 768) ? 768 : 128;
-            switch (cap) {
-                case 8: e = launch_sorted_sweep<8>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
-                case 16: e = launch_sorted_sweep<16>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
-                case 24: e = launch_sorted_sweep<24>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
-                default: e = launch_sorted_sweep<32>(mode, spec.fma, h == 0, a, tri.data(), threads, nb, s); break;
-            }
-        } else if (cap == 0) {
+        trace_begin(p, (cap == 0 ? 200 : (h == 0 ? 0 : 100)) + h, s);
+        if (cap == 0) {
             GenericArgs a{};
-            a.in = in; a.out = out; a.mat = p->d_mat; a.line_off = p->d_line_off;
+            a.in = in; a.out = out; a.mat = d_mat; a.line_off = p->d_line_off;
             a.perm_in = gather ? p->d_perm : nullptr;
             a.perm_out = scatter ? p->d_perm : nullptr;
             a.stride = p->N; a.n1 = n1; a.mode = mode; a.fma = spec.fma ? 1 : 0;
             if (h == 0) { a.ent = nullptr; a.num_threads = int32_t(p->N1); }
             else {
                 const DeviceDim &d = p->dd[h];
+                if (!d.thr_fib) { set_error("force_generic: the fibre CSR of this plan was not uploaded (set larger than 2^20 elements)"); return LPFNT_EUNSUPPORTED; }
                 a.thr_fib = d.thr_fib; a.thr_start = d.thr_start; a.fib_ptr = d.fib_ptr; a.ent = d.ent;
                 a.num_threads = d.num_threads;
             }
             e = launch_generic_sweep(a, nb, s);
         } else if (h == 0) {
             LineSweepArgs a{in, out, p->d_line_off, gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->d_line_order, p->N, int32_t(p->N1)};
-            switch (cap) {
-                case 8: e = launch_line_sweep<8>(mode, spec.fma, a, tri.data(), nb, s); break;
-                case 16: e = launch_line_sweep<16>(mode, spec.fma, a, tri.data(), nb, s); break;
-                case 24: e = launch_line_sweep<24>(mode, spec.fma, a, tri.data(), nb, s); break;
-                default: e = launch_line_sweep<32>(mode, spec.fma, a, tri.data(), nb, s); break;
-            }
-        } else if (tiles) {
-            const DeviceDim &d = p->dd[h];
-            TileSweepArgs a{in, out, d.tile_rec, d.tile_elem, d.ent, d.row_pos, d.elem_row, d.items, d.rows0,
-                            gather ? p->d_perm : nullptr, scatter ? p->d_perm : nullptr, p->N, p->debug_skip};
-            switch (cap) {
-                case 8: e = launch_tile_sweep<8>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
-                case 16: e = launch_tile_sweep<16>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
-                case 24: e = launch_tile_sweep<24>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
-                default: e = launch_tile_sweep<32>(mode, spec.fma, fuse0, a, tri.data(), p->max_line, d.num_tiles, nb, s); break;
-            }
+            LAUNCH_CAP(cap, launch_line_sweep<8>(mode, spec.fma, a, tri, nb, s), launch_line_sweep<16>(mode, spec.fma, a, tri, nb, s),
+                       launch_line_sweep<24>(mode, spec.fma, a, tri, nb, s), launch_line_sweep<32>(mode, spec.fma, a, tri, nb, s))
         } else {
             if (gather) { set_error("internal: gather is only fused into the coordinate-0 sweep"); return LPFNT_EINVAL; }
             const DeviceDim &d = p->dd[h];
-            if (p->use_groups && d.groups) {
-                GroupSweepArgs ga{in, out, d.groups, d.group_t, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups, p->use_two_lanes, p->use_cta_cap ? d.group_cta_cap : nullptr};
-                switch (cap) {
-                    case 8: e = launch_group_sweep<8>(mode, spec.fma, ga, tri.data(), nb, s); break;
-                    case 16: e = launch_group_sweep<16>(mode, spec.fma, ga, tri.data(), nb, s); break;
-                    case 24: e = launch_group_sweep<24>(mode, spec.fma, ga, tri.data(), nb, s); break;
-                    default: e = launch_group_sweep<32>(mode, spec.fma, ga, tri.data(), nb, s); break;
-                }
-                trace_end(p, s);
-                p->launches += 1;
-                if (e != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
-                continue;
-            }
-            FibreSweepArgs a{in, out, d.thr_fib, d.thr_start, d.fib_ptr, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_threads};
-            switch (cap) {
-                case 8: e = launch_fibre_sweep<8>(mode, spec.fma, a, tri.data(), nb, s); break;
-                case 16: e = launch_fibre_sweep<16>(mode, spec.fma, a, tri.data(), nb, s); break;
-                case 24: e = launch_fibre_sweep<24>(mode, spec.fma, a, tri.data(), nb, s); break;
-                default: e = launch_fibre_sweep<32>(mode, spec.fma, a, tri.data(), nb, s); break;
-            }
+            GroupSweepArgs ga{in, out, d.groups, d.group_t, d.ent, scatter ? p->d_perm : nullptr, p->N, d.num_groups, p->use_cta_cap ? d.group_cta_cap : nullptr};
+            LAUNCH_CAP(cap, launch_group_sweep<8>(mode, spec.fma, ga, tri, nb, s), launch_group_sweep<16>(mode, spec.fma, ga, tri, nb, s),
+                       launch_group_sweep<24>(mode, spec.fma, ga, tri, nb, s), launch_group_sweep<32>(mode, spec.fma, ga, tri, nb, s))
         }
         trace_end(p, s);
         p->launches += 1;
@@ -323,51 +280,6 @@ int launch_dim(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const do
     return LPFNT_OK;
 }
 
-// One pipelined row-tile pass along coordinate h (optionally fused with coordinate 0): src -> dst.
-int launch_pipe(lpfnt_plan *p, const SweepSpec &spec, int h, bool fuse0, const double *src, double *dst, int64_t batch, cudaStream_t s) {
-    const int n1 = p->n + 1;
-    const int mode = sweep_mode(spec);
-    const DeviceDim &d = p->dd[h];
-    const int len = std::max(d.max_lines, fuse0 ? p->max_line : 0);
-    const int cap = pick_cap(std::max(len, 1));
-    std::vector<double> tri;
-    repack(spec.packed, n1, spec.kind, cap, tri);
-    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 20)) {
-        const int nb = int(std::min<int64_t>(int64_t(1) << 20, batch - b0));
-        const int64_t units = int64_t(d.num_tiles) * nb;
-        int upc = int((units + 2 * p->num_sms - 1) / (2 * p->num_sms));
-        upc = std::max(1, std::min(upc, kPipeMaxUnits));
-        const int grid = int((units + upc - 1) / upc);
-        PipeArgs a{src + b0 * p->N, dst + b0 * p->N, d.tile_rec, d.tile_elem, d.row_desc, d.elem_row, d.items, d.rows0,
-                   p->N, d.num_tiles, nb, fuse0 ? 1 : 0, upc, p->debug_skip};
-        cudaError_t e = cudaSuccess;
-        trace_begin(p, (fuse0 ? 700 : 600) + h, s);
-        switch (cap) {
-            case 8: e = launch_tile_pipe<8>(mode, spec.fma, a, tri.data(), grid, s); break;
-            case 16: e = launch_tile_pipe<16>(mode, spec.fma, a, tri.data(), grid, s); break;
-            case 24: e = launch_tile_pipe<24>(mode, spec.fma, a, tri.data(), grid, s); break;
-            default: e = launch_tile_pipe<32>(mode, spec.fma, a, tri.data(), grid, s); break;
-        }
-        trace_end(p, s);
-        p->launches += 1;
-        if (e != cudaSuccess) { set_error(std::string("pipe kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
-    }
-    return LPFNT_OK;
-}
-
-int launch_perm(lpfnt_plan *p, const double *src, double *dst, int64_t batch, bool scatter, cudaStream_t s) {
-    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
-        const int nb = int(std::min<int64_t>(65535, batch - b0));
-        trace_begin(p, scatter ? 801 : 800, s);
-        cudaError_t e = launch_permute(src + b0 * p->N, dst + b0 * p->N, p->d_perm, p->N, p->N, nb, scatter, s);
-        trace_end(p, s);
-        p->launches += 1;
-        if (e != cudaSuccess) { set_error(std::string("permute launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
-    }
-    return LPFNT_OK;
-}
-
-// Whole-function path (m <= 3, everything of one function in shared memory): one launch per transform.
 // Slab tables for k_slab: runs of consecutive planes (= fibres of coordinate 1) with at most
 // kSlabThreads lines, kSlabThreads coordinate-1 element-fibres and kSlabElems elements.
 int build_slabs(lpfnt_plan *p, const HostIndex &hx) {
@@ -417,7 +329,7 @@ int build_slabs(lpfnt_plan *p, const HostIndex &hx) {
             }
         }
         // length classes of 8, natural (plane, lane) order inside a class: a warp's lanes stay on few lines (coalesced
-        // result stores, fewer bank conflicts) at ~10 % less uniform lengths -- same trade as for k_whole2
+        // result stores, fewer bank conflicts) at ~10 % less uniform lengths
         std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return (x.first + 7) / 8 > (y.first + 7) / 8; });
         for (auto &e : tmp) item1.push_back(e.second);
         desc.push_back(d);
@@ -438,8 +350,7 @@ int build_slabs(lpfnt_plan *p, const HostIndex &hx) {
 int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
     const int mode = sweep_mode(spec);
     const int cap = pick_cap(std::max(p->slabs.max_t, 1));
-    std::vector<double> tri;
-    repack(spec.packed, p->n + 1, spec.kind, cap, tri);
+    const double *tri = operator_tri(p, spec.op, cap);
     SlabArgs a{};
     a.slab = p->slabs.d_desc; a.item0 = p->slabs.d_item0; a.item1 = p->slabs.d_item1; a.line_off = p->d_line_off;
     a.perm_in = gather ? p->d_perm : nullptr;
@@ -452,12 +363,8 @@ int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
         const int grid = int(std::min<int64_t>(units, int64_t(p->num_sms) * 3));
         cudaError_t e = cudaSuccess;
         trace_begin(p, 1601, s);
-        switch (cap) {
-            case 8: e = launch_slab<8>(mode, spec.fma, a, tri.data(), grid, s); break;
-            case 16: e = launch_slab<16>(mode, spec.fma, a, tri.data(), grid, s); break;
-            case 24: e = launch_slab<24>(mode, spec.fma, a, tri.data(), grid, s); break;
-            default: e = launch_slab<32>(mode, spec.fma, a, tri.data(), grid, s); break;
-        }
+        LAUNCH_CAP(cap, launch_slab<8>(mode, spec.fma, a, tri, grid, s), launch_slab<16>(mode, spec.fma, a, tri, grid, s),
+                   launch_slab<24>(mode, spec.fma, a, tri, grid, s), launch_slab<32>(mode, spec.fma, a, tri, grid, s))
         trace_end(p, s);
         p->launches += 1;
         if (e != cudaSuccess) { set_error(std::string("slab kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
@@ -465,207 +372,88 @@ int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
     return LPFNT_OK;
 }
 
-// Box layout for k_whole3, built from A alone (any downward-closed set with m = 2 or 3).
-int build_box(lpfnt_plan *p, const int64_t *A, const int64_t *perm, const HostIndex &hx) {
-    const int m = p->m;
-    const int64_t N = p->N, N1 = p->N1;
-    if (m < 2 || m > 3 || N >= 65536 || N1 > kW3Compute || p->n + 1 > kMaxRegT) return LPFNT_OK;
-    // (a0, a1, k): m = 3 -> alpha; m = 2 -> (alpha_0, 0, alpha_1)
-    auto a1_of = [&](int64_t i) { return m == 3 ? int(A[i * m + 1]) : 0; };
-    auto k_of = [&](int64_t i) { return int(A[i * m + m - 1]); };
-    int K = 0;
-    for (int64_t i = 0; i < N; ++i) K = std::max(K, k_of(i) + 1);
-    if (K > 32) return LPFNT_OK;
-    std::vector<int> nl(K, 0), len0(K, 0);
-    for (int64_t i = 0; i < N; ++i) {
-        const int k = k_of(i);
-        nl[k] = std::max(nl[k], a1_of(i) + 1);
-        len0[k] = std::max(len0[k], int(A[i * m]) + 1);
+// ---- whole-function kernel (k_whole): tables, eligibility, launch ----
+void free_whole(lpfnt_plan *p) {
+    lpfnt_plan::Whole &W = p->whole;
+    cudaFree(W.d_items); cudaFree(W.d_seo);
+    W.d_items = nullptr; W.d_seo = nullptr;
+    W.h = WholeHost();
+}
+
+int upload_whole(lpfnt_plan *p) {
+    lpfnt_plan::Whole &W = p->whole;
+    free_whole(p);
+    if (!p->hx) return LPFNT_OK;
+    // two CTAs of 384 threads per SM when two functions (plus tables) fit into shared memory, else one CTA of 768
+    int threads = p->whole_threads;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int tg = threads > 0 ? threads : (pass == 0 ? 384 : 768);
+        p->hx->build_whole(tg, p->whole_order);
+        const WholeHost &h = p->hx->whole;
+        if (!h.ok) return LPFNT_OK;
+        W.smem_bytes = whole_smem_bytes(int(p->N), int(h.items.size()), int(h.seo.size()), p->has_perm);
+        if (threads > 0 || W.smem_bytes <= size_t(kWholeSmemPerCta) || pass == 1) break;
     }
-    lpfnt_plan::Box &B = p->box;
-    int64_t W = 0, L = 0;
-    for (int k = 0; k < 32; ++k) { B.c.P[k] = 0; B.c.S[k] = 0; B.c.L[k] = 0; }
-    for (int k = 0; k < K; ++k) {
-        B.c.P[k] = int32_t(W); B.c.S[k] = len0[k] | 1; B.c.L[k] = int32_t(L);
-        W += int64_t(nl[k]) * B.c.S[k];
-        L += nl[k];
-    }
-    if (L != N1 || W > 65535 || whole3_smem_bytes(int(W), int(N1), int(N), perm != nullptr) > size_t(227) * 1024) return LPFNT_OK;
-    std::vector<uint16_t> lo16(N1);
-    std::vector<int2> pline(N1);
-    // line lengths per (a1, k)
-    std::vector<std::vector<int>> len(K);
-    for (int k = 0; k < K; ++k) len[k].assign(nl[k], 0);
-    for (int64_t l = 0; l < N1; ++l) {
-        const int64_t i = hx.line_off[l];
-        lo16[l] = uint16_t(i);
-        if (B.c.L[k_of(i)] + a1_of(i) != l) return LPFNT_OK;  // lines are not plane-major (cannot happen for colex order)
-        len[k_of(i)][a1_of(i)] = int(hx.line_off[l + 1] - hx.line_off[l]);
-        pline[l] = make_int2(int(B.c.P[k_of(i)] + a1_of(i) * B.c.S[k_of(i)]) | (len[k_of(i)][a1_of(i)] << 16), int(i));
-    }
-    auto sort_desc = [](std::vector<std::pair<int, uint32_t>> &v, std::vector<uint32_t> &out) {
-        std::stable_sort(v.begin(), v.end(), [](const std::pair<int, uint32_t> &x, const std::pair<int, uint32_t> &y) { return x.first > y.first; });
-        out.resize(v.size());
-        for (size_t q = 0; q < v.size(); ++q) out[q] = v[q].second;
-    };
-    std::vector<std::pair<int, uint32_t>> tmp;
-    std::vector<uint32_t> item[3];
-    int max_t = 0;
-    // coordinate 0: lines
-    for (int k = 0; k < K; ++k)
-        for (int a1 = 0; a1 < nl[k]; ++a1) {
-            const int t = len[k][a1];
-            tmp.push_back({t, uint32_t(B.c.P[k] + a1 * B.c.S[k]) | (uint32_t(t) << 16)});
-            max_t = std::max(max_t, t);
-        }
-    sort_desc(tmp, item[0]);
-    // coordinate 1 (m = 3): (a0, k)
-    tmp.clear();
-    if (m == 3)
-        for (int k = 0; k < K; ++k)
-            for (int a0 = 0; a0 < len0[k]; ++a0) {
-                int t = 0;
-                while (t < nl[k] && len[k][t] > a0) ++t;
-                tmp.push_back({t, uint32_t(B.c.P[k] + a0) | (uint32_t(B.c.S[k]) << 16) | (uint32_t(t) << 24)});
-                max_t = std::max(max_t, t);
-            }
-    sort_desc(tmp, item[1]);
-    // last coordinate: (a0, a1) of plane 0
-    tmp.clear();
-    for (int a1 = 0; a1 < nl[0]; ++a1)
-        for (int a0 = 0; a0 < len[0][a1]; ++a0) {
-            int t = 0;
-            while (t < K && a1 < nl[t] && len[t][a1] > a0) ++t;
-            tmp.push_back({t, uint32_t(a0) | (uint32_t(a1) << 8) | (uint32_t(t) << 16)});
-            max_t = std::max(max_t, t);
-        }
-    sort_desc(tmp, item[2]);
-    for (int h = 0; h < 3; ++h) if (item[h].size() > size_t(kW3Compute)) return LPFNT_OK;
+    W.h = p->hx->whole;
+    if (W.smem_bytes > size_t(W.h.threads == 384 ? kWholeSmemPerCta : kWholeSmemLimit)) { W.h = WholeHost(); return LPFNT_OK; }
     int rc;
-    for (int h = 0; h < 3; ++h) {
-        B.n_item[h] = int32_t(item[h].size());
-        if ((rc = upload(&B.d_item[h], item[h].data(), item[h].size(), p))) return rc;
-    }
-    if ((rc = upload(&B.d_pline, pline.data(), pline.size(), p))) return rc;
-    if ((rc = upload(&B.d_line_off16, lo16.data(), lo16.size(), p))) return rc;
-    if (perm) {
-        std::vector<uint16_t> p16(N);
-        for (int64_t i = 0; i < N; ++i) p16[i] = uint16_t(perm[i]);
-        if ((rc = upload(&B.d_perm16, p16.data(), p16.size(), p))) return rc;
-    }
-    B.n_box = int32_t(W); B.max_t = max_t; B.ok = true;
+    if ((rc = upload(&W.d_items, W.h.items.data(), W.h.items.size(), p))) return rc;
+    if ((rc = upload(&W.d_seo, W.h.seo.data(), W.h.seo.size(), p))) return rc;
+    W.total_items = int32_t(W.h.items.size());
+    W.seo_len = int32_t(W.h.seo.size());
+    W.h.items.clear(); W.h.items.shrink_to_fit();
+    W.h.seo.clear(); W.h.seo.shrink_to_fit();
     return LPFNT_OK;
 }
 
-bool whole3_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims) {
-    if (p->use_whole != 3 || p->force_generic || !p->box.ok || int(dims.size()) != p->m) return false;
+bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, int64_t batch) {
+    const lpfnt_plan::Whole &W = p->whole;
+    if (!W.h.ok || p->force_generic || int(dims.size()) != p->m) return false;
+    // automatic: enough functions to fill a few SMs (a single function would run on ONE SM) and enough items to keep
+    // most of a CTA busy
+    const bool want = p->use_whole == 1 || (p->use_whole == -1 && batch >= 8 && 3 * W.h.max_items >= 2 * W.h.threads);
+    if (!want) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
     if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
-    return pick_cap(std::max(p->box.max_t, 1)) > 0;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return false;    // bulk copies need a 16-byte aligned batch
+    return true;
 }
 
-int launch_whole3_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+    lpfnt_plan::Whole &W = p->whole;
     const int mode = sweep_mode(spec);
-    const int cap = pick_cap(std::max(p->box.max_t, 1));
-    std::vector<double> tri;
-    repack(spec.packed, p->n + 1, spec.kind, cap, tri);
-    const lpfnt_plan::Box &B = p->box;
-    Whole3Args a{};
-    a.item0 = B.d_item[0]; a.item1 = B.d_item[1]; a.item2 = B.d_item[2];
-    a.pline = B.d_pline; a.perm16 = B.d_perm16; a.line_off16 = B.d_line_off16;
-    a.gather = gather ? 1 : 0; a.scatter = scatter ? 1 : 0;
-    a.n_elem = int32_t(p->N); a.n_box = B.n_box; a.n_lines = int32_t(p->N1); a.m = p->m;
-    a.n_item0 = B.n_item[0]; a.n_item1 = B.n_item[1]; a.n_item2 = B.n_item[2];
-    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
-        const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
-        a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
-        const int grid = int(std::min<int64_t>(nb, p->num_sms));
-        cudaError_t e = cudaSuccess;
-        trace_begin(p, 1500, s);
-        switch (cap) {
-            case 8: e = launch_whole3<8>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
-            case 16: e = launch_whole3<16>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
-            case 24: e = launch_whole3<24>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
-            default: e = launch_whole3<32>(mode, spec.fma, a, B.c, tri.data(), grid, s); break;
-        }
-        trace_end(p, s);
-        p->launches += 1;
-        if (e != cudaSuccess) { set_error(std::string("whole-function (box) kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
-    }
-    return LPFNT_OK;
-}
-
-// second-generation whole-function kernel: every sweep in one round, bulk copies need 16-byte granules
-bool whole2_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, int64_t batch) {
-    // automatic: enough items to fill the CTA and enough functions to fill a few SMs -- a single function would run on ONE
-    // SM (measured at d=3, n=30, B=1: 29 us against 24 us for the per-coordinate kernels spread over the GPU)
-    const bool want = p->use_whole == 2 || (p->use_whole == -1 && p->N1 >= 512 && batch >= 8);
-    if (!want || p->force_generic || p->m < 2 || p->m > 3 || int(dims.size()) != p->m) return false;
-    for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
-    if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
-    if (p->N >= 65536 || p->N1 > kWhole2Threads || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
-    if (reinterpret_cast<uintptr_t>(in) & 15) return false;
-    for (int h = 1; h < p->m; ++h) if (!p->dd[h].sorted || !p->dd[h].ent_off16 || p->dd[h].num_sorted != p->N1) return false;
-    return whole2_smem_bytes(int(p->N), int(p->N1), p->has_perm) <= size_t(227) * 1024;
-}
-
-bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims) {
-    if (p->use_whole != 1 || p->force_generic || p->m > 3 || int(dims.size()) != p->m) return false;
-    for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
-    if (spec.kind != LPFNT_LOWER) return false;
-    if (p->N >= 65536 || p->n + 1 > kMaxRegT || !p->d_sorted0) return false;
-    for (int h = 1; h < p->m; ++h) if (!p->dd[h].sorted || !p->dd[h].ent_off16) return false;
-    return whole_smem_bytes(int(p->N), int(p->N1)) <= size_t(220) * 1024;
-}
-
-int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s, bool gen2 = false) {
-    const int n1 = p->n + 1;
-    const int mode = sweep_mode(spec);
-    int len = p->max_line;
-    for (int h = 1; h < p->m; ++h) len = std::max(len, p->dd[h].max_lines);
-    const int cap = pick_cap(std::max(len, 1));
-    std::vector<double> tri;
-    repack(spec.packed, n1, spec.kind, cap, tri);
+    const int cap = pick_cap(std::max(W.h.max_t, 1));
+    const double *tri = operator_tri(p, spec.op, cap);
     WholeArgs a{};
-    a.in = src; a.out = dst;
-    a.sorted[0] = p->d_sorted0; a.ent_off[0] = nullptr;
-    for (int h = 1; h < p->m; ++h) { a.sorted[h] = p->dd[h].sorted; a.ent_off[h] = p->dd[h].ent_off16; }
-    if (gen2) {
-        const int ord = spec.fma ? p->w2_order_fma : p->w2_order_exact;
-        for (int h = 0; h < p->m; ++h)
-            if (p->w2_items[h][(ord >> (2 * h)) & 3]) a.sorted[h] = p->w2_items[h][(ord >> (2 * h)) & 3];
-    }
-    a.perm_in = gather ? p->d_perm : nullptr;
-    a.perm_out = scatter ? p->d_perm : nullptr;
-    a.n_elem = int(p->N); a.n_lines = int(p->N1); a.m = p->m;
-    a.dbg = gen2 ? p->d_timeline : nullptr;
-    const size_t smem = whole_smem_bytes(int(p->N), int(p->N1));
-    const int threads = spec.fma ? 256 : 384;
-    int occ = int(std::min<size_t>((size_t(227) * 1024) / (smem + 1024), size_t(2048 / threads)));
-    occ = std::max(1, std::min(occ, spec.fma ? 2 : 1 + (smem < 100 * 1024)));
+    a.items = W.d_items; a.seo = W.d_seo; a.perm16 = W.d_perm16;
+    a.total_items = W.total_items; a.seo_len = W.seo_len;
+    for (int h = 0; h < 3; ++h) { a.item_off[h] = W.h.item_off[h]; a.n_items[h] = W.h.n_items[h]; }
+    a.gather = gather ? 1 : 0; a.scatter = scatter ? 1 : 0;
+    a.n_elem = int32_t(p->N); a.m = p->m;
+    a.dbg = p->d_timeline;
+    const bool timeline = p->d_timeline != nullptr;
+    // rows folded side by side: 4 for the fused form (its chains are latency bound: 56 -> 75 % of the FP64 pipe at 12
+    // warps per SM, tools/probe4.cu), 2 for the exact form (twice the instructions per term already)
+    const int rows = p->whole_rows > 0 ? p->whole_rows : (spec.fma ? 4 : 2);
+    const int key = ((cap / 8 - 1) * 5 + (mode == kLowerMatvec ? (spec.fma ? 1 : 0) : mode == kUpperMatvec ? (spec.fma ? 3 : 2) : 4)) * 3 +
+                    (W.h.threads == 384 ? 0 : 1) + (rows == 4 ? 1 : 0) * 0;  // < 64
+    const int key2 = key + (rows == 4 ? 60 : 0);
+    const bool set_attr = timeline || key2 >= 64 || !(W.attr_set >> key2 & 1u);
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
         a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
-        const int grid = int(std::min<int64_t>(nb, int64_t(p->num_sms) * (gen2 ? 1 : occ)));
+        const int per_sm = W.h.threads == 384 ? 2 : 1;
+        const int grid = int(std::min<int64_t>(nb, int64_t(per_sm) * p->num_sms));
         cudaError_t e = cudaSuccess;
-        trace_begin(p, gen2 ? 1400 : 1000, s);
-        if (gen2) {
-            switch (cap) {
-                case 8: e = launch_whole2<8>(mode, spec.fma, a, tri.data(), grid, s); break;
-                case 16: e = launch_whole2<16>(mode, spec.fma, a, tri.data(), grid, s); break;
-                case 24: e = launch_whole2<24>(mode, spec.fma, a, tri.data(), grid, s); break;
-                default: e = launch_whole2<32>(mode, spec.fma, a, tri.data(), grid, s); break;
-            }
-        } else
-        switch (cap) {
-            case 8: e = launch_whole<8>(mode, spec.fma, a, tri.data(), grid, s); break;
-            case 16: e = launch_whole<16>(mode, spec.fma, a, tri.data(), grid, s); break;
-            case 24: e = launch_whole<24>(mode, spec.fma, a, tri.data(), grid, s); break;
-            default: e = launch_whole<32>(mode, spec.fma, a, tri.data(), grid, s); break;
-        }
+        trace_begin(p, 1400, s);
+        LAUNCH_CAP(cap, launch_whole<8>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
+                   launch_whole<16>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
+                   launch_whole<24>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
+                   launch_whole<32>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s))
         trace_end(p, s);
         p->launches += 1;
         if (e != cudaSuccess) { set_error(std::string("whole-function kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+        if (!timeline && key2 < 64) W.attr_set |= uint64_t(1) << key2;
     }
     return LPFNT_OK;
 }
@@ -673,123 +461,74 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
 // Device-resident pipeline: sweeps along `dims` (ascending), optional colex gather on the way
 // in and scatter on the way out.  in/out may alias.
 //
-// Pass plan: with the tile kernels the coordinate-0 sweep rides along with the coordinate-1 pass
-// (one pass fewer); every remaining coordinate is one pass.  Passes 2.. run in place.  A batched
-// multi-pass transform is cut into chunks of functions of ~l2_chunk_bytes so that the passes
-// after the first find their input in the 126 MB L2 instead of HBM.
+// Pass plan: the whole-function kernel when it applies (one pass); else the slab kernel takes coordinates 0 and 1 in one
+// pass and every remaining coordinate is one pass.  Passes 2.. run in place.
 struct Pass { int h; bool fuse0; };
 
 int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, double *out,
-               int64_t batch, bool gather, bool scatter, cudaStream_t s, int mid_slot = 2) {
+               int64_t batch, bool gather, bool scatter, cudaStream_t s, int lane) {
+    const int mid_slot = 3 * lane + 2;
     gather = gather && p->has_perm;
     scatter = scatter && p->has_perm;
     if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
-    if (spec.solve && spec.kind == LPFNT_UPPER && (p->use_tiles || p->use_sorted || p->use_planes || p->use_pipe)) {
-        set_error("the upper triangular solve only runs on the default line/group kernels");
-        return LPFNT_EUNSUPPORTED;
-    }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
-    if (whole3_ok(p, spec, dims)) {
+    if (whole_ok(p, spec, dims, in, batch)) {
         // in-place is safe: a function is complete in shared memory / registers before its first store
-        return launch_whole3_fn(p, spec, in, out, batch, gather, scatter, s);
-    }
-    if (whole2_ok(p, spec, dims, in, batch)) {
-        // in-place is safe: a function is complete in shared memory / registers before its first store
-        return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s, true);
-    }
-    if (whole_ok(p, spec, dims)) {
-        // in-place is safe: a function is read completely into shared memory before it is written
         return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s);
     }
     std::vector<Pass> passes;
     {
         size_t q = 0;
-        const bool can_plane = !p->force_generic && p->use_planes && p->num_planes > 0 && pick_cap(std::max(p->max_line, p->dd[1].max_lines)) > 0;
-        const bool can_slab = p->use_slab && p->slabs.ok && !p->force_generic && !p->use_tiles && !p->use_planes && !p->use_sorted && p->m >= 2 &&
+        const bool can_slab = p->use_slab && p->slabs.ok && !p->force_generic && p->m >= 2 &&
                               pick_cap(std::max(p->slabs.max_t, 1)) > 0 && !(spec.solve && spec.kind == LPFNT_UPPER);
-        const bool can_tile = can_slab || can_plane || !p->force_generic && !p->use_sorted && p->use_tiles && p->m >= 2 && p->dd[1].num_tiles > 0 &&
-                              pick_cap(std::max(p->max_line, p->dd[1].max_lines)) > 0;
-        if (dims.size() >= 2 && dims[0] == 0 && dims[1] == 1 && can_tile) { passes.push_back({1, true}); q = 2; }
+        if (dims.size() >= 2 && dims[0] == 0 && dims[1] == 1 && can_slab) { passes.push_back({1, true}); q = 2; }
         for (; q < dims.size(); ++q) passes.push_back({dims[q], false});
     }
     const int np = int(passes.size());
     const size_t fbytes = size_t(p->N) * sizeof(double);
-    int64_t chunk = batch;
     const bool permuting = gather || scatter;
-    bool pipe = !p->force_generic && p->use_tiles && p->use_pipe && !p->use_sorted;
-    for (const Pass &ps : passes)
-        pipe = pipe && ps.h >= 1 && p->dd[ps.h].num_tiles > 0 && pick_cap(std::max(p->dd[ps.h].max_lines, ps.fuse0 ? p->max_line : 0)) > 0;
-    const int nlaunch = np + (pipe ? int(gather) + int(scatter) : 0);
-    if (nlaunch >= 2 && p->l2_chunk_bytes > 0) chunk = std::max<int64_t>(1, std::min<int64_t>(batch, p->l2_chunk_bytes / int64_t(fbytes)));
-
-    if (pipe) {
-        // stand-alone permutation passes + pipelined sweeps; everything after the first launch of a
-        // chunk finds its input in L2
-        const bool need_mid = permuting;  // the permutation passes never run in place
-        double *mid_base = nullptr;
-        if (need_mid) { int rc = ensure_ws(p, mid_slot, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[mid_slot]; }
-        for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
-            const int64_t nb = std::min(chunk, batch - b0);
-            const double *cur = in + b0 * p->N;
-            double *cout = out + b0 * p->N;
-            if (gather) { int rc = launch_perm(p, cur, mid_base, nb, false, s); if (rc) return rc; cur = mid_base; }
-            for (int q = 0; q < np; ++q) {
-                double *dst = (q == np - 1 && !scatter) ? cout : (need_mid ? mid_base : cout);
-                int rc = launch_pipe(p, spec, passes[q].h, passes[q].fuse0, cur, dst, nb, s);
-                if (rc) return rc;
-                cur = dst;
-            }
-            if (scatter) { int rc = launch_perm(p, cur, cout, nb, true, s); if (rc) return rc; }
-        }
-        return LPFNT_OK;
-    }
-
     // a permuting pass must not run in place; with >= 2 passes the middle buffer absorbs that
     const bool need_mid = (np == 1) ? (permuting && in == out) : (scatter || (permuting && in == out));
     double *mid_base = nullptr;
-    if (need_mid) { int rc = ensure_ws(p, mid_slot, size_t(chunk) * fbytes); if (rc) return rc; mid_base = p->ws[mid_slot]; }
-    for (int64_t b0 = 0; b0 < batch; b0 += chunk) {
-        const int64_t nb = std::min(chunk, batch - b0);
-        const double *cin = in + b0 * p->N;
-        double *cout = out + b0 * p->N;
-        if (np == 1) {
-            double *dst = need_mid ? mid_base : cout;
-            int rc = launch_dim(p, spec, passes[0].h, passes[0].fuse0, cin, dst, nb, gather, scatter, s);
-            if (rc) return rc;
-            if (dst != cout) CK(cudaMemcpyAsync(cout, dst, size_t(nb) * fbytes, cudaMemcpyDeviceToDevice, s));
-            continue;
-        }
-        double *mid = need_mid ? mid_base : cout;
-        for (int q = 0; q < np; ++q) {
-            const bool first = (q == 0), last = (q == np - 1);
-            int rc = launch_dim(p, spec, passes[q].h, passes[q].fuse0, first ? cin : mid, last ? cout : mid, nb,
-                                first && gather, last && scatter, s);
-            if (rc) return rc;
-        }
+    if (need_mid) { int rc = ensure_ws(p, mid_slot, size_t(batch) * fbytes); if (rc) return rc; mid_base = p->ws[mid_slot]; }
+    if (np == 1) {
+        double *dst = need_mid ? mid_base : out;
+        int rc = launch_dim(p, spec, passes[0].h, passes[0].fuse0, in, dst, batch, gather, scatter, s);
+        if (rc) return rc;
+        if (dst != out) CK(cudaMemcpyAsync(out, dst, size_t(batch) * fbytes, cudaMemcpyDeviceToDevice, s));
+        return LPFNT_OK;
     }
-    return LPFNT_OK;
-}
-
-// Host-pointer front end: stage through ws[0]/ws[1] in chunks of functions.
-// Sequence of sweeps (one spec = one triangular operator applied along `dims`); gather rides on the first,
-// scatter on the last.
-int run_specs(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vector<int> &dims, const double *in, double *out,
-              int64_t batch, bool gather, bool scatter, cudaStream_t s, int mid_slot) {
-    const int ns = int(specs.size());
-    for (int i = 0; i < ns; ++i) {
-        int rc = run_device(p, specs[i], dims, i == 0 ? in : out, out, batch, gather && i == 0, scatter && i == ns - 1, s, mid_slot);
+    double *mid = need_mid ? mid_base : out;
+    for (int q = 0; q < np; ++q) {
+        const bool first = (q == 0), last = (q == np - 1);
+        int rc = launch_dim(p, spec, passes[q].h, passes[q].fuse0, first ? in : mid, last ? out : mid, batch,
+                            first && gather, last && scatter, s);
         if (rc) return rc;
     }
     return LPFNT_OK;
 }
 
-int run_any(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vector<int> &dims, const double *in, double *out,
+// Sequence of sweeps (one spec = one triangular operator applied along `dims`); gather rides on the first,
+// scatter on the last.
+int run_specs(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vector<int> &dims, const double *in, double *out,
+              int64_t batch, bool gather, bool scatter, cudaStream_t s, int lane) {
+    const int ns = int(specs.size());
+    for (int i = 0; i < ns; ++i) {
+        int rc = run_device(p, specs[i], dims, i == 0 ? in : out, out, batch, gather && i == 0, scatter && i == ns - 1, s, lane);
+        if (rc) return rc;
+    }
+    return LPFNT_OK;
+}
+
+// Host-pointer front end: stage through the lanes' workspaces in chunks of functions.
+int run_any(lpfnt_plan *p, std::vector<SweepSpec> specs, const std::vector<int> &dims, const double *in, double *out,
             int64_t batch, bool gather, bool scatter, int on_device, void *stream) {
     if (!p || !in || !out || batch < 1) { set_error("null pointer or empty batch"); return LPFNT_EINVAL; }
     for (const SweepSpec &sp : specs)
         if (!sp.packed) { set_error("the plan was created without the matrix this operation needs"); return LPFNT_EINVAL; }
     CK(cudaSetDevice(p->device));
-    if (on_device) return run_specs(p, specs, dims, in, out, batch, gather, scatter, static_cast<cudaStream_t>(stream), 2);
+    for (SweepSpec &sp : specs) sp.op = find_operator(p, sp.packed, sp.kind);
+    if (on_device) return run_specs(p, specs, dims, in, out, batch, gather, scatter, static_cast<cudaStream_t>(stream), 0);
     // Host pointers: cut the batch into chunks and run them on two lanes (streams) with their own staging
     // buffers, so that the H2D copy of chunk i+1 overlaps the sweeps and the D2H copy of chunk i
     // (PCIe is full duplex; the copies dominate this path by an order of magnitude).
@@ -813,7 +552,7 @@ int run_any(lpfnt_plan *p, const std::vector<SweepSpec> &specs, const std::vecto
         const int l = (lanes == 2) ? (i & 1) : 0;
         cudaStream_t s = l ? p->stream2 : p->stream;
         CK(cudaMemcpyAsync(p->ws[3 * l], in + b0 * p->N, size_t(nb) * fbytes, cudaMemcpyHostToDevice, s));
-        int rc = run_specs(p, specs, dims, p->ws[3 * l], p->ws[3 * l + 1], nb, gather, scatter, s, 3 * l + 2);
+        int rc = run_specs(p, specs, dims, p->ws[3 * l], p->ws[3 * l + 1], nb, gather, scatter, s, l);
         if (rc) return rc;
         CK(cudaMemcpyAsync(out + b0 * p->N, p->ws[3 * l + 1], size_t(nb) * fbytes, cudaMemcpyDeviceToHost, s));
     }
@@ -903,102 +642,36 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         DeviceDim &d = p->dd[h];
         d.num_threads = int32_t(D.num_threads);
         d.max_lines = D.max_lines;
-        if ((rc = upload(&d.thr_fib, D.thr_fib.data(), D.thr_fib.size(), p))) return fail(rc);
-        if ((rc = upload(&d.thr_start, D.thr_start.data(), D.thr_start.size(), p))) return fail(rc);
-        if ((rc = upload(&d.fib_ptr, D.fib_ptr.data(), D.fib_ptr.size(), p))) return fail(rc);
         static_assert(sizeof(FibEnt) == sizeof(int2), "FibEnt must match int2");
-        if ((rc = upload(&d.ent, reinterpret_cast<const int2 *>(D.ent.data()), D.ent.size(), p))) return fail(rc);
         static_assert(sizeof(SortedItem) == sizeof(int2), "SortedItem must match int2");
-        if (!D.sorted.empty()) {
-            d.num_sorted = int32_t(D.sorted.size());
-            if ((rc = upload(&d.sorted, reinterpret_cast<const int2 *>(D.sorted.data()), D.sorted.size(), p))) return fail(rc);
+        const bool generic_only = D.groups.empty();  // fibres too long for the register kernels
+        if (generic_only || hx.max_line > kMaxRegT || D.max_lines > kMaxRegT || N <= (int64_t(1) << 20)) {
+            // the generic kernel walks the plain CSR
+            if ((rc = upload(&d.thr_fib, D.thr_fib.data(), D.thr_fib.size(), p))) return fail(rc);
+            if ((rc = upload(&d.thr_start, D.thr_start.data(), D.thr_start.size(), p))) return fail(rc);
+            if ((rc = upload(&d.fib_ptr, D.fib_ptr.data(), D.fib_ptr.size(), p))) return fail(rc);
         }
-        if (N < 65536) {
-            std::vector<uint16_t> eo(D.ent.size());
-            for (size_t r = 0; r < D.ent.size(); ++r) eo[r] = uint16_t(D.ent[r].off);
-            if ((rc = upload(&d.ent_off16, eo.data(), eo.size(), p))) return fail(rc);
-        }
+        if ((rc = upload(&d.ent, reinterpret_cast<const int2 *>(D.ent.data()), D.ent.size(), p))) return fail(rc);
         if (!D.groups.empty()) {
             d.num_groups = int32_t(D.groups.size());
             if ((rc = upload(&d.groups, reinterpret_cast<const int2 *>(D.groups.data()), D.groups.size(), p))) return fail(rc);
             if ((rc = upload(&d.group_t, D.group_t.data(), D.group_t.size(), p))) return fail(rc);
             if ((rc = upload(&d.group_cta_cap, D.group_cta_cap.data(), D.group_cta_cap.size(), p))) return fail(rc);
         }
-        if (!D.tile_fib.empty()) {
-            d.num_tiles = int32_t(D.tile_fib.size()) - 1;
-            if ((rc = upload(&d.tile_fib, D.tile_fib.data(), D.tile_fib.size(), p))) return fail(rc);
-            if ((rc = upload(&d.items, D.items.data(), D.items.size(), p))) return fail(rc);
-            if ((rc = upload(&d.rows0, D.rows0.data(), D.rows0.size(), p))) return fail(rc);
-            std::vector<int4> rec(d.num_tiles);
-            for (int tl = 0; tl < d.num_tiles; ++tl) {
-                const int f0 = D.tile_fib[tl], f1 = D.tile_fib[tl + 1];
-                rec[tl] = make_int4(D.fib_ptr[f0], D.fib_ptr[f1] - D.fib_ptr[f0], D.thr_start[f0], D.thr_start[f1] - D.thr_start[f0]);
-            }
-            if ((rc = upload(&d.tile_rec, rec.data(), rec.size(), p))) return fail(rc);
-            {
-                std::vector<int2> te(d.num_tiles);
-                for (int tl = 0; tl < d.num_tiles; ++tl) te[tl] = make_int2(D.tile_elem[tl], D.tile_nelem[tl]);
-                if ((rc = upload(&d.tile_elem, te.data(), te.size(), p))) return fail(rc);
-            }
-            if ((rc = upload(&d.row_pos, D.row_pos.data(), D.row_pos.size(), p))) return fail(rc);
-            {
-                std::vector<int2> rd(D.ent.size());
-                for (size_t r = 0; r < D.ent.size(); ++r) rd[r] = make_int2(D.ent[r].off - int(D.row_pos[r]), int(D.row_pos[r]));
-                if ((rc = upload(&d.row_desc, rd.data(), rd.size(), p))) return fail(rc);
-            }
-            if ((rc = upload(&d.elem_row, D.elem_row.data(), D.elem_row.size(), p))) return fail(rc);
-        }
     }
     if ((rc = upload(&p->d_line_order, hx.line_order.data(), hx.line_order.size(), p))) return fail(rc);
-    if (m >= 2 && hx.dims[1].max_lines <= 32 && hx.max_line <= 32) {
-        // the fibres of coordinate 1 are the planes; their rows are consecutive lines, so the CSR of the
-        // fibres is also the CSR of lines per plane
-        const DimTable &D1 = hx.dims[1];
-        bool consecutive = true;
-        for (int32_t f = 0; f < D1.num_fibres && consecutive; ++f)
-            for (int32_t r = D1.fib_ptr[f]; r < D1.fib_ptr[f + 1]; ++r)
-                if (D1.ent[r].off != hx.line_off[r]) { consecutive = false; break; }
-        if (consecutive) {
-            if ((rc = upload(&p->d_plane_line, D1.fib_ptr.data(), D1.fib_ptr.size(), p))) return fail(rc);
-            p->num_planes = D1.num_fibres;
-        }
-    }
-    if (m >= 2 && m <= 3 && N < 65536 && hx.max_line <= 255) {
-        for (int h = 0; h < m; ++h) {
-            std::vector<std::pair<int, int2>> nat;  // natural order with heights
-            if (h == 0) {
-                for (int64_t l = 0; l < hx.N1; ++l) {
-                    const int t = hx.line_off[l + 1] - hx.line_off[l];
-                    nat.push_back({t, make_int2(hx.line_off[l], t << 8)});
-                }
-            } else {
-                const DimTable &D = hx.dims[h];
-                if (D.max_lines > 255) continue;
-                for (int32_t f = 0; f < D.num_fibres; ++f) {
-                    const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
-                    const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
-                    for (int32_t lane = 0; lane < lanes; ++lane) {
-                        int32_t t = 0;
-                        while (t < nl && D.ent[p0 + t].len > lane) ++t;
-                        nat.push_back({t, make_int2(p0, lane | (t << 8))});
-                    }
-                }
-            }
-            const int cls[4] = {1, 8, 16, 1 << 20};
-            for (int v = 0; v < 4; ++v) {
-                std::vector<std::pair<int, int2>> s = nat;
-                const int q = cls[v];
-                std::stable_sort(s.begin(), s.end(), [q](const std::pair<int, int2> &x, const std::pair<int, int2> &y) { return (x.first + q - 1) / q > (y.first + q - 1) / q; });
-                std::vector<int2> out(s.size());
-                for (size_t i = 0; i < s.size(); ++i) out[i] = s[i].second;
-                if ((rc = upload(&p->w2_items[h][v], out.data(), out.size(), p))) return fail(rc);
-            }
-        }
-    }
-    if ((rc = build_box(p, A, perm, hx))) return fail(rc);
     if ((rc = build_slabs(p, hx))) return fail(rc);
-    if (!hx.sorted0.empty())
-        if ((rc = upload(&p->d_sorted0, reinterpret_cast<const int2 *>(hx.sorted0.data()), hx.sorted0.size(), p))) return fail(rc);
+    if (hx.whole.ok || (m >= 2 && m <= 3 && N < 65536)) {
+        // whole-function kernel: keep the index structure (its tables can be re-built with other options)
+        p->hx = new HostIndex(hx);
+        p->hx->whole = WholeHost();
+        if (perm) {
+            std::vector<uint16_t> p16(N);
+            for (int64_t i = 0; i < N; ++i) p16[i] = uint16_t(perm[i]);
+            if ((rc = upload(&p->whole.d_perm16, p16.data(), p16.size(), p))) return fail(rc);
+        }
+        if ((rc = upload_whole(p))) return fail(rc);
+    }
     if (!hx.eval_block.empty()) {
         static_assert(sizeof(EvalBlock) == sizeof(int4), "EvalBlock must match int4");
         if ((rc = upload(&p->d_eval_line, reinterpret_cast<const int2 *>(hx.eval_line.data()), hx.eval_line.size(), p))) return fail(rc);
@@ -1007,16 +680,16 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if (cudaMalloc(reinterpret_cast<void **>(&p->d_cpad), sizeof(double) * size_t(hx.eval_padded + 4)) != cudaSuccess) { set_error("cudaMalloc(cpad) failed"); return fail(LPFNT_ENOMEM); }
         p->table_bytes += int64_t(sizeof(double)) * (hx.eval_padded + 4);
     }
-    if (!hx.line_alpha.empty())
-        if ((rc = upload(&p->d_line_alpha, hx.line_alpha.data(), hx.line_alpha.size(), p))) return fail(rc);
-    // the generic eval needs A on the device; keep a host copy when that path can be reached
-    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255 || N * m <= (int64_t(1) << 26)) p->hA.assign(A, A + N * m);
-    if (nodes && (rc = upload(&p->d_nodes, nodes, size_t(n + 1), p))) return fail(rc);
-    {
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_mat), sizeof(double) * ts);
-        if (e != cudaSuccess) { set_error("cudaMalloc(d_mat) failed"); return fail(LPFNT_ENOMEM); }
-        p->table_bytes += sizeof(double) * ts;
+    if (!hx.line_alpha.empty()) {
+        // the eval kernel stages the alpha bytes in 4-byte words: pad the table so that its last word is complete
+        std::vector<uint8_t> al(hx.line_alpha);
+        al.resize(((al.size() + 3) & ~size_t(3)) + 4, 0);
+        if ((rc = upload(&p->d_line_alpha, al.data(), al.size(), p))) return fail(rc);
     }
+    // the generic eval needs A on the device: keep a host copy when the fast path cannot run, or when the set is small
+    // enough for the copy not to matter (force_generic in the tests)
+    if (n + 1 > kMaxRegT || m > kEvalMaxM || n > 255 || N * m <= (int64_t(1) << 20)) p->hA.assign(A, A + N * m);
+    if (nodes && (rc = upload(&p->d_nodes, nodes, size_t(n + 1), p))) return fail(rc);
     {
         cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking);
@@ -1030,16 +703,17 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
-    for (int h = 0; h < 3; ++h) cudaFree(p->box.d_item[h]);
-    for (int h = 0; h < 3; ++h) for (int v = 0; v < 4; ++v) cudaFree(p->w2_items[h][v]);
+    free_whole(p);
+    cudaFree(p->whole.d_perm16);
+    delete p->hx;
     cudaFree(p->d_timeline);
     cudaFree(p->slabs.d_desc); cudaFree(p->slabs.d_item0); cudaFree(p->slabs.d_item1);
-    cudaFree(p->box.d_pline); cudaFree(p->box.d_perm16); cudaFree(p->box.d_line_off16);
-    cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_sorted0); cudaFree(p->d_plane_line); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
-    cudaFree(p->d_nodes); cudaFree(p->d_mat);
+    cudaFree(p->d_line_off); cudaFree(p->d_perm); cudaFree(p->d_line_order); cudaFree(p->d_line_alpha); cudaFree(p->d_A);
+    cudaFree(p->d_nodes);
+    for (OperatorCache *oc : p->ops) { cudaFree(oc->d_packed); delete oc; }
     for (int h = 0; h <= kMaxDim; ++h) {
         cudaFree(p->dd[h].thr_fib); cudaFree(p->dd[h].thr_start); cudaFree(p->dd[h].fib_ptr); cudaFree(p->dd[h].ent);
-        cudaFree(p->dd[h].tile_fib); cudaFree(p->dd[h].items); cudaFree(p->dd[h].rows0); cudaFree(p->dd[h].tile_rec); cudaFree(p->dd[h].sorted); cudaFree(p->dd[h].ent_off16); cudaFree(p->dd[h].groups); cudaFree(p->dd[h].group_t); cudaFree(p->dd[h].group_cta_cap); cudaFree(p->dd[h].tile_elem); cudaFree(p->dd[h].row_pos); cudaFree(p->dd[h].row_desc); cudaFree(p->dd[h].elem_row);
+        cudaFree(p->dd[h].groups); cudaFree(p->dd[h].group_t); cudaFree(p->dd[h].group_cta_cap);
     }
     for (int s = 0; s < 6; ++s) cudaFree(p->ws[s]);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1056,21 +730,21 @@ int64_t lpfnt_plan_device_bytes(const lpfnt_plan *p) {
 }
 int64_t lpfnt_plan_launch_count(const lpfnt_plan *p) { return p ? p->launches : 0; }
 
+constexpr int kTimelineCount = 4 * 2 * 24 * kWholeStamps;
+
 int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_planes") == 0) { p->use_planes = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "host_chunk_bytes") == 0) { p->host_chunk_bytes = value <= 0 ? 0 : std::max<int64_t>(value, 1 << 16); return LPFNT_OK; }
-    if (std::strcmp(name, "w2_order_exact") == 0) { p->w2_order_exact = int(value); return LPFNT_OK; }
-    if (std::strcmp(name, "w2_order_fma") == 0) { p->w2_order_fma = int(value); return LPFNT_OK; }
     if (std::strcmp(name, "use_cta_cap") == 0) { p->use_cta_cap = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "timeline") == 0) {
+        CK(cudaSetDevice(p->device));
         if (value && !p->d_timeline) {
-            CK(cudaMalloc(reinterpret_cast<void **>(&p->d_timeline), 4 * 24 * 16 * sizeof(long long)));
-            CK(cudaMemset(p->d_timeline, 0, 4 * 24 * 16 * sizeof(long long)));
-        } else if (!value && p->d_timeline) { cudaFree(p->d_timeline); p->d_timeline = nullptr; }
+            CK(cudaMalloc(reinterpret_cast<void **>(&p->d_timeline), kTimelineCount * sizeof(long long)));
+            CK(cudaMemset(p->d_timeline, 0, kTimelineCount * sizeof(long long)));
+        } else if (!value && p->d_timeline) { CK(cudaDeviceSynchronize()); cudaFree(p->d_timeline); p->d_timeline = nullptr; }
         return LPFNT_OK;
     }
     if (std::strcmp(name, "use_slab") == 0) {
@@ -1078,14 +752,15 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
         if (value == 2 && p->slabs.n_slabs > 0) p->slabs.ok = true;  // 2: force the slab kernel even for sparsely filled slabs (tests)
         return LPFNT_OK;
     }
-    if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < -1 ? -1 : (value > 3 ? 3 : value); return LPFNT_OK; }
-    if (std::strcmp(name, "use_two_lanes") == 0) { p->use_two_lanes = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_groups") == 0) { p->use_groups = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_sorted") == 0) { p->use_sorted = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "debug_skip") == 0) { p->debug_skip = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_tiles") == 0) { p->use_tiles = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "use_pipe") == 0) { p->use_pipe = value ? 1 : 0; return LPFNT_OK; }
-    if (std::strcmp(name, "l2_chunk_bytes") == 0) { p->l2_chunk_bytes = value; return LPFNT_OK; }
+    if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
+    if (std::strcmp(name, "whole_rows") == 0) { p->whole_rows = (value == 2 || value == 4) ? int(value) : -1; return LPFNT_OK; }
+    if (std::strcmp(name, "whole_threads") == 0 || std::strcmp(name, "whole_order") == 0) {
+        if (name[6] == 't') p->whole_threads = (value == 384 || value == 768) ? int(value) : -1;
+        else p->whole_order = value < 0 ? kWholeDefaultOrder : int(value & 63);
+        CK(cudaSetDevice(p->device));
+        CK(cudaDeviceSynchronize());  // the tables may be in use
+        return upload_whole(p);
+    }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;
 }
@@ -1127,7 +802,7 @@ int lpfnt_plan_timeline_read(lpfnt_plan *p, long long *out, int count) {
     if (!p || !out || !p->d_timeline) { set_error("timeline: not enabled"); return LPFNT_EINVAL; }
     CK(cudaSetDevice(p->device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out, p->d_timeline, sizeof(long long) * size_t(std::min(count, 4 * 24 * 16)), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, p->d_timeline, sizeof(long long) * size_t(std::min(count, kTimelineCount)), cudaMemcpyDeviceToHost));
     return LPFNT_OK;
 }
 

@@ -140,7 +140,7 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
     for (int64_t e = 0; e < N; ++e) {
         const int64_t a0 = A[e * m];
         if (a0 == 0) line_off.push_back(static_cast<int32_t>(e));
-        else if (a0 != e - line_off.back()) {
+        else if (line_off.empty() || a0 != e - line_off.back()) {
             set_error("HostIndex: A is not colex ordered (coordinate 0 must count up along each line)");
             return false;
         }
@@ -252,117 +252,6 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
     }
 
 
-    // ---- row tiles: consecutive fibres grouped so that a CTA stages <= kTileRows lines in shared
-    //      memory and owns <= kTileItems element-fibres; inside a tile the element-fibres (and, for
-    //      the fused coordinate-0 sweep, the rows) are ordered by length, longest first, so that the
-    //      32 lanes of a warp run triangles of (nearly) the same size. ----
-    for (int h = 1; h < m; ++h) {
-        DimTable &D = dims[h];
-        if (D.max_lines > 255 || max_line > 255) continue;  // descriptors pack lengths into 8 bits
-        D.tile_fib.clear();
-        D.tile_fib.push_back(0);
-        int32_t rows = 0, items = 0, elems = 0;
-        for (int32_t f = 0; f < D.num_fibres; ++f) {
-            const int32_t fr = D.fib_ptr[f + 1] - D.fib_ptr[f];
-            const int32_t fi = D.thr_start[f + 1] - D.thr_start[f];
-            int32_t fe = 0;
-            for (int32_t r = D.fib_ptr[f]; r < D.fib_ptr[f + 1]; ++r) fe += D.ent[r].len;
-            if (f > D.tile_fib.back() && (rows + fr > kTileRows || items + fi > kTileItems || elems + fe > kTileElems)) {
-                D.tile_fib.push_back(f);
-                rows = 0;
-                items = 0;
-                elems = 0;
-            }
-            rows += fr;
-            items += fi;
-            elems += fe;
-        }
-        D.tile_fib.push_back(D.num_fibres);
-        const int32_t ntiles = static_cast<int32_t>(D.tile_fib.size()) - 1;
-        D.items.resize(D.num_threads);
-        D.rows0.resize(N1);
-        // packed staging layout: the rows of a tile sit back to back in shared memory; row_pos = packed
-        // offset of each row, elem_row = for every packed element its row (uint8), tile_elem = CSR of
-        // packed elements per tile.  Copies in and out of the tile are then one element per lane.
-        D.row_pos.resize(N1);
-        D.elem_row.assign(size_t(N) + 4 * size_t(ntiles), 0);  // every tile's map starts 4-byte aligned
-        D.tile_elem.assign(ntiles + 1, 0);
-        D.tile_nelem.assign(ntiles, 0);
-        {
-            int64_t e = 0;
-            for (int32_t tl = 0; tl < ntiles; ++tl) {
-                e = (e + 3) & ~int64_t(3);
-                D.tile_elem[tl] = static_cast<int32_t>(e);
-                const int32_t ra = D.fib_ptr[D.tile_fib[tl]], rb = D.fib_ptr[D.tile_fib[tl + 1]];
-                int32_t pos = 0;
-                for (int32_t r = ra; r < rb; ++r) {
-                    D.row_pos[r] = static_cast<uint16_t>(pos);
-                    for (int32_t c = 0; c < D.ent[r].len; ++c) D.elem_row[e++] = static_cast<uint8_t>(r - ra);
-                    pos += D.ent[r].len;
-                }
-                D.tile_nelem[tl] = pos;
-            }
-            D.tile_elem[ntiles] = static_cast<int32_t>(e);
-            D.elem_row.resize(size_t((e + 3) & ~int64_t(3)));
-        }
-        std::vector<uint32_t> tmp;
-        for (int32_t tl = 0; tl < ntiles; ++tl) {
-            const int32_t f0 = D.tile_fib[tl], f1 = D.tile_fib[tl + 1];
-            const int32_t r0 = D.fib_ptr[f0], r1 = D.fib_ptr[f1];
-            const int32_t i0 = D.thr_start[f0];
-            // element-fibres of the tile
-            tmp.clear();
-            for (int32_t f = f0; f < f1; ++f) {
-                const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
-                const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
-                for (int32_t lane = 0; lane < lanes; ++lane) {
-                    int32_t t = 0;
-                    while (t < nl && D.ent[p0 + t].len > lane) ++t;
-                    tmp.push_back(uint32_t(p0 - r0) | (uint32_t(lane) << 16) | (uint32_t(t) << 24));
-                }
-            }
-            std::stable_sort(tmp.begin(), tmp.end(), [](uint32_t a, uint32_t b) { return (a >> 24) > (b >> 24); });
-            std::copy(tmp.begin(), tmp.end(), D.items.begin() + i0);
-            // rows of the tile (coordinate-0 sweep)
-            tmp.clear();
-            for (int32_t r = r0; r < r1; ++r) tmp.push_back(uint32_t(r - r0) | (uint32_t(D.ent[r].len) << 24));
-            std::stable_sort(tmp.begin(), tmp.end(), [](uint32_t a, uint32_t b) { return (a >> 24) > (b >> 24); });
-            std::copy(tmp.begin(), tmp.end(), D.rows0.begin() + r0);
-        }
-    }
-
-    // ---- globally length-sorted element-fibres (k_sweep_sorted): per coordinate h >= 1 the items
-    //      {first entry of the fibre in ent, lane | t << 8}, longest first (stable: neighbours in
-    //      the natural order stay neighbours inside a length class); for coordinate 0 the lines
-    //      {element offset, t}. ----
-    {
-        auto sort_desc = [](std::vector<SortedItem> &v) {
-            std::stable_sort(v.begin(), v.end(), [](const SortedItem &a, const SortedItem &b) { return (a.y >> 8) > (b.y >> 8); });
-        };
-        sorted0.clear();
-        if (max_line <= 255) {
-            sorted0.resize(N1);
-            for (int64_t l = 0; l < N1; ++l) sorted0[l] = SortedItem{line_off[l], (line_off[l + 1] - line_off[l]) << 8};
-            sort_desc(sorted0);
-        }
-        for (int h = 1; h < m; ++h) {
-            DimTable &D = dims[h];
-            D.sorted.clear();
-            if (D.max_lines > 255 || max_line > 255) continue;
-            D.sorted.reserve(D.num_threads);
-            for (int32_t f = 0; f < D.num_fibres; ++f) {
-                const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
-                const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
-                for (int32_t lane = 0; lane < lanes; ++lane) {
-                    int32_t t = 0;
-                    while (t < nl && D.ent[p0 + t].len > lane) ++t;
-                    D.sorted.push_back(SortedItem{p0, lane | (t << 8)});
-                }
-            }
-            sort_desc(D.sorted);
-        }
-    }
-
     // ---- lane groups (k_sweep_groups): every fibre's lanes are cut into runs of <= kGroupLanes
     //      consecutive lanes; the runs are ordered by height (longest element-fibre first), so that
     //      the four runs sharing a warp execute triangles of similar size while every run still reads
@@ -448,7 +337,73 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         for (int64_t l = 0; l < N1; ++l)
             for (int j = 1; j < m; ++j) line_alpha[l * (m - 1) + (j - 1)] = static_cast<uint8_t>(key(l, j));
     }
+    // ---- last coordinate of every line + the item tables of the whole-function kernel ----
+    line_last.clear();
+    whole = WholeHost();
+    if (n <= 255 && m >= 2) {
+        line_last.resize(size_t(N1));
+        for (int64_t l = 0; l < N1; ++l) line_last[l] = static_cast<uint8_t>(key(l, m - 1));
+        build_whole(768, kWholeDefaultOrder);
+    }
     return true;
+}
+
+void HostIndex::build_whole(int threads, int order) {
+    whole = WholeHost();
+    WholeHost &W = whole;
+    if (m < 2 || m > 3 || N >= 65536 || max_line > kMaxRegT || (threads != 384 && threads != 768)) return;
+    for (int h = 1; h < m; ++h)
+        if (dims[h].max_lines > kMaxRegT) return;
+    const int TG = threads;
+    W.threads = threads;
+    auto rounds = [&](int64_t items) { return int32_t((items + TG - 1) / TG) * TG; };
+    // seo: per coordinate h >= 1 the line offsets in fibre order
+    std::vector<int32_t> seo_off(m, 0);
+    for (int h = 1; h < m; ++h) {
+        seo_off[h] = int32_t(W.seo.size());
+        for (const FibEnt &en : dims[h].ent) W.seo.push_back(uint16_t(en.off));
+    }
+    if (W.seo.size() > 65536) return;
+    struct Item { int t; uint32_t w; };
+    for (int h = 0; h < m; ++h) {
+        std::vector<Item> nat;
+        if (h == 0) {
+            for (int64_t l = 0; l < N1; ++l) {
+                const int t = line_off[l + 1] - line_off[l];
+                nat.push_back({t, uint32_t(line_off[l]) | (uint32_t(t) << 16)});
+            }
+        } else {
+            const DimTable &D = dims[h];
+            for (int32_t f = 0; f < D.num_fibres; ++f) {
+                const int32_t p0 = D.fib_ptr[f], nl = D.fib_ptr[f + 1] - p0;
+                const int32_t lanes = D.thr_start[f + 1] - D.thr_start[f];
+                for (int32_t lane = 0; lane < lanes; ++lane) {
+                    int32_t t = 0;
+                    while (t < nl && D.ent[p0 + t].len > lane) ++t;
+                    nat.push_back({t, uint32_t(seo_off[h] + p0) | (uint32_t(t) << 16) | (uint32_t(lane) << 22)});
+                }
+            }
+        }
+        const int cls[4] = {1, 8, 16, 1 << 20};
+        const int q = cls[(order >> (2 * h)) & 3];
+        std::stable_sort(nat.begin(), nat.end(), [q](const Item &a, const Item &b) { return (a.t + q - 1) / q > (b.t + q - 1) / q; });
+        for (const Item &it : nat) W.max_t = std::max(W.max_t, it.t);
+        const int32_t nit = int32_t(nat.size()), padded = rounds(nit);
+        W.item_off[h] = int32_t(W.items.size());
+        W.n_items[h] = padded;
+        W.max_items = std::max(W.max_items, nit);
+        for (int32_t r0 = 0; r0 < padded; r0 += TG) {
+            for (int tid = 0; tid < TG; ++tid) {
+                // chunks of 32 items (longest first) are dealt to the warps in SNAKE order over the four SM sub-partitions
+                // (warp w runs on sub-partition w % 4): 0 1 2 3 / 3 2 1 0 / ...
+                const int w = tid >> 5, grp = w >> 2;
+                const int chunk = grp * 4 + ((grp & 1) ? 3 - (w & 3) : (w & 3));
+                const int32_t src = r0 + chunk * 32 + (tid & 31);
+                W.items.push_back(src < nit ? nat[src].w : 0u);
+            }
+        }
+    }
+    W.ok = true;
 }
 
 }  // namespace lpfnt
@@ -472,23 +427,17 @@ bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t
     if (what == LPFNT_TAB_LINE_ALPHA) return set(x.line_alpha.data(), 1, x.line_alpha.size(), int64_t(x.line_alpha.size()));
     if (what == LPFNT_TAB_LEVEL_SIZE) return set(x.level_size.data(), 8, x.level_size.size(), int64_t(x.level_size.size()));
     if (what == LPFNT_TAB_LINE_ORDER) return set(x.line_order.data(), 4, x.line_order.size(), int64_t(x.line_order.size()));
-    if (what == LPFNT_TAB_SORTED && h == 0) return set(x.sorted0.data(), 8, x.sorted0.size(), int64_t(2 * x.sorted0.size()));
+    if (what == LPFNT_TAB_WHOLE_ITEMS) return set(x.whole.items.data(), 4, x.whole.items.size(), int64_t(x.whole.items.size()));
+    if (what == LPFNT_TAB_WHOLE_SEO) return set(x.whole.seo.data(), 2, x.whole.seo.size(), int64_t(x.whole.seo.size()));
+    if (what == LPFNT_TAB_LINE_LAST) return set(x.line_last.data(), 1, x.line_last.size(), int64_t(x.line_last.size()));
     if (h < 1 || h >= x.m) return false;
     const DimTable &D = x.dims[h];
     if (what == LPFNT_TAB_FIB_PTR) return set(D.fib_ptr.data(), 4, D.fib_ptr.size(), int64_t(D.fib_ptr.size()));
     if (what == LPFNT_TAB_FIB_ENT) return set(D.ent.data(), 8, D.ent.size(), int64_t(2 * D.ent.size()));
     if (what == LPFNT_TAB_THR_START) return set(D.thr_start.data(), 4, D.thr_start.size(), int64_t(D.thr_start.size()));
     if (what == LPFNT_TAB_THR_FIB) return set(D.thr_fib.data(), 4, D.thr_fib.size(), int64_t(D.thr_fib.size()));
-    if (what == LPFNT_TAB_SORTED) return set(D.sorted.data(), 8, D.sorted.size(), int64_t(2 * D.sorted.size()));
     if (what == LPFNT_TAB_GROUPS) return set(D.groups.data(), 8, D.groups.size(), int64_t(2 * D.groups.size()));
     if (what == LPFNT_TAB_GROUP_T) return set(D.group_t.data(), 1, D.group_t.size(), int64_t(D.group_t.size()));
-    if (what == LPFNT_TAB_TILE_FIB) return set(D.tile_fib.data(), 4, D.tile_fib.size(), int64_t(D.tile_fib.size()));
-    if (what == LPFNT_TAB_TILE_ITEMS) return set(D.items.data(), 4, D.items.size(), int64_t(D.items.size()));
-    if (what == LPFNT_TAB_TILE_ROWS0) return set(D.rows0.data(), 4, D.rows0.size(), int64_t(D.rows0.size()));
-    if (what == LPFNT_TAB_TILE_ROWPOS) return set(D.row_pos.data(), 2, D.row_pos.size(), int64_t(D.row_pos.size()));
-    if (what == LPFNT_TAB_TILE_ELEMROW) return set(D.elem_row.data(), 1, D.elem_row.size(), int64_t(D.elem_row.size()));
-    if (what == LPFNT_TAB_TILE_ELEM) return set(D.tile_elem.data(), 4, D.tile_elem.size(), int64_t(D.tile_elem.size()));
-    if (what == LPFNT_TAB_TILE_NELEM) return set(D.tile_nelem.data(), 4, D.tile_nelem.size(), int64_t(D.tile_nelem.size()));
     return false;
 }
 }  // namespace
@@ -574,6 +523,20 @@ int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **
     return LPFNT_OK;
 }
 int lpfnt_index_destroy(lpfnt_index *index) { delete index; return LPFNT_OK; }
+int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order) {
+    if (!index) { set_error("index is null"); return LPFNT_EINVAL; }
+    if (threads != 384 && threads != 768) { set_error("whole_build: threads must be 384 or 768"); return LPFNT_EINVAL; }
+    index->hx.build_whole(threads, order < 0 ? kWholeDefaultOrder : order);
+    return LPFNT_OK;
+}
+int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta) {
+    if (!index || !meta) { set_error("whole_meta: bad arguments"); return LPFNT_EINVAL; }
+    const WholeHost &W = index->hx.whole;
+    int q = 0;
+    meta[q++] = W.ok ? 1 : 0; meta[q++] = W.threads; meta[q++] = W.max_t; meta[q++] = W.max_items;
+    for (int h = 0; h < 3; ++h) { meta[q++] = W.item_off[h]; meta[q++] = W.n_items[h]; }
+    return q;  // 10 entries
+}
 int64_t lpfnt_index_size(const lpfnt_index *index, int what, int h) {
     const void *p; size_t b; int64_t c;
     if (!index || !table_view(index, what, h, &p, &b, &c)) { set_error("index_size: no such table"); return LPFNT_EINVAL; }

@@ -15,9 +15,8 @@ constexpr int kEvalBlockElems = 2048;  // padded doubles per block (16 KB)
 constexpr int kGroupLanes = 8;   // consecutive lanes of a fibre that stay together in k_sweep_groups
 constexpr int kLineChunk = 128;  // lines per CTA of k_sweep_lines
 constexpr int kGroupClass = 4;  // lane groups of k_sweep_groups are ordered by height class of this many rows
-constexpr int kTileRows = 256;  // lines staged in shared memory by one CTA of the tile kernels
-constexpr int kTileItems = 256; // element-fibres per CTA (two per thread, 128 threads)
-constexpr int kTileElems = 5120; // packed elements per CTA (40 KB; two data buffers + descriptor ring = 110 KB -> 2 CTAs/SM)
+constexpr int kWholeSmemLimit = 227 * 1024;   // one CTA per SM
+constexpr int kWholeSmemPerCta = 113 * 1024;  // two CTAs per SM (each reserves 1 KB besides its dynamic shared memory)
 
 void set_error(const std::string &msg);
 
@@ -45,19 +44,23 @@ struct DimTable {
     std::vector<FibEnt> ent;             // N_1 entries
     std::vector<int32_t> thr_start;      // num_fibres + 1, prefix sum of lanes per fibre
     std::vector<int32_t> thr_fib;        // num_threads, thread -> fibre
-    // row tiles (see HostIndex::build): tile -> fibre range; per tile the element-fibres and rows
-    // sorted by length.  item = row_rel | lane << 16 | t << 24 ; row0 = row_rel | len << 24
-    std::vector<SortedItem> sorted;      // num_threads: element-fibres, longest first
     std::vector<uint8_t> group_t;        // 8 per group: height of every lane of the run
     std::vector<SortedItem> groups;      // lane runs {first ent entry, lane0 | t << 8 | lanes << 16}, tallest first
     std::vector<uint8_t> group_cta_cap;  // per 16 consecutive runs (one CTA of k_sweep_groups): tallest height
-    std::vector<int32_t> tile_fib;       // num_tiles + 1
-    std::vector<uint32_t> items;         // num_threads (indexed like the threads: thr_start[f0] + j)
-    std::vector<uint32_t> rows0;         // N_1 (indexed like ent: fib_ptr[f0] + j)
-    std::vector<uint16_t> row_pos;       // N_1: packed shared-memory offset of every row inside its tile
-    std::vector<uint8_t> elem_row;       // N: row (relative to the tile) of every packed element
-    std::vector<int32_t> tile_elem;      // num_tiles + 1: start of each tile in elem_row (4-aligned)
-    std::vector<int32_t> tile_nelem;     // num_tiles: packed elements of each tile
+};
+
+// Item tables of the whole-function kernel (k_whole, whole_kernel.cuh), built from the index structure alone.
+// Per coordinate one list of 32-bit words: bits 0..15 = element offset of the line (coordinate 0) or first entry of the
+// fibre in seo (coordinate h >= 1: element k of the item sits at seo[entry + k] + lane), bits 16..21 = length t,
+// bits 22..31 = lane a_0; already in THREAD order: rounds of `threads` items, inside a round chunks of 32 items dealt
+// to the warps in snake order over the four SM sub-partitions.  Empty slots are 0 (t = 0).
+struct WholeHost {
+    bool ok = false;
+    int threads = 0;                       // threads per CTA the lists were laid out for (384: two CTAs per SM, 768: one)
+    int32_t item_off[3] = {0, 0, 0}, n_items[3] = {0, 0, 0};
+    int32_t max_t = 0, max_items = 0;
+    std::vector<uint32_t> items;
+    std::vector<uint16_t> seo;
 };
 
 // Host-side index structure derived from the multi-index array A (colex order).
@@ -68,7 +71,8 @@ struct HostIndex {
     std::vector<int32_t> line_off;       // N_1 + 1 (cs_T)
     std::vector<int64_t> level_size;     // m + 1: N_0, N_1, ..., N_{m-1}, 1
     std::vector<DimTable> dims;          // index h = 0..m-1 (entry 0 unused)
-    std::vector<SortedItem> sorted0;     // N_1: the lines, longest first (coordinate 0)
+    std::vector<uint8_t> line_last;      // N_1: a_{m-1} of every line (m >= 2, n <= 255)
+    WholeHost whole;
     std::vector<int32_t> line_order;     // N_1: lines ordered by length inside every chunk of kLineChunk
     std::vector<SortedItem> eval_line;   // N_1: {padded coefficient offset, line length}
     std::vector<EvalBlock> eval_block;   // blocks of lines staged together by the eval kernel
@@ -76,6 +80,10 @@ struct HostIndex {
     std::vector<uint8_t> line_alpha;     // N_1 * (m-1): (a_1..a_{m-1}) of every line, for eval (n <= 255)
     // returns false (and sets the error) if A is not a colex-ordered downward-closed set
     bool build(const int64_t *A, int64_t N, int m, int n);
+    // (re)build `whole` for CTAs of `threads` threads (384 or 768); order = 2 bits per coordinate: 0 strict length order,
+    // 1 / 2 length classes of 8 / 16 (natural order inside a class), 3 natural
+    void build_whole(int threads, int order);
 };
+constexpr int kWholeDefaultOrder = 0 | (2 << 2) | (2 << 4);
 
 }  // namespace lpfnt

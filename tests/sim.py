@@ -72,53 +72,34 @@ def sweep(x, tabs, h, M, mode, n1):
     return out
 
 
-def sweep_tiles(x, tabs, h, M, mode, n1, dim0):
-    """Emulates k_sweep_tiles: per tile the rows are staged PACKED (back to back), an optional sweep
-    along coordinate 0 over the rows (sorted row list), then the sweep along h over the sorted items;
-    copies in and out go through the element->row map exactly like the kernel."""
-    tile_fib = tabs.table(nat.TAB_TILE_FIB, h)
-    ptr = tabs.table(nat.TAB_FIB_PTR, h)
-    ent = tabs.table(nat.TAB_FIB_ENT, h)
-    tstart = tabs.table(nat.TAB_THR_START, h)
-    items = tabs.table(nat.TAB_TILE_ITEMS, h)
-    rows0 = tabs.table(nat.TAB_TILE_ROWS0, h)
-    row_pos = tabs.table(nat.TAB_TILE_ROWPOS, h).astype(np.int64)
-    elem_row = tabs.table(nat.TAB_TILE_ELEMROW, h).astype(np.int64)
-    tile_elem = tabs.table(nat.TAB_TILE_ELEM, h)
-    tile_nelem = tabs.table(nat.TAB_TILE_NELEM, h)
-    out = np.full_like(x, np.nan)
-    for tl in range(len(tile_fib) - 1):
-        f0, f1 = tile_fib[tl], tile_fib[tl + 1]
-        r0, r1 = ptr[f0], ptr[f1]
-        i0, i1 = tstart[f0], tstart[f1]
-        e0 = tile_elem[tl]
-        e1 = e0 + tile_nelem[tl]
-        assert e0 % 4 == 0
-        R, E = r1 - r0, e1 - e0
-        assert R <= 256 and i1 - i0 <= 256 and E <= 5120
-        pos = row_pos[r0:r1]
-        delta = ent[r0:r1, 0] - pos
-        src = np.arange(E) + delta[elem_row[e0:e1]]
-        buf = x[src].copy()
-        if dim0:
-            d = rows0[r0:r1]
-            rr, tt = (d & 0xFFFF).astype(int), (d >> 24).astype(int)
-            assert sorted(rr) == list(range(R)) and np.all(np.diff(tt) <= 0)
-            idx = pos[rr][:, None] + np.arange(n1)[None, :]
-            valid = np.arange(n1)[None, :] < tt[:, None]
-            X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
-            Y = apply_tri(X, M, mode)
-            buf[idx[valid]] = Y[valid]
-        d = items[i0:i1]
-        rr, ll, tt = (d & 0xFFFF).astype(int), ((d >> 16) & 0xFF).astype(int), (d >> 24).astype(int)
-        assert np.all(np.diff(tt) <= 0)
-        kk = np.arange(n1)[None, :]
-        valid = kk < tt[:, None]
-        rowidx = np.where(valid, rr[:, None] + kk, 0)
-        idx = pos[rowidx] + ll[:, None]
+def whole_function(x, tabs: nat.IndexTables, M, n1, mode="lower"):
+    """Emulates k_whole (lpfun_b200/csrc/whole_kernel.cuh) from its REAL item tables: the function is staged, the
+    coordinates 0 .. m-2 run in place over the item lists (rounds of `threads` items in thread order), the last
+    coordinate reads its fibres and writes the result."""
+    meta = tabs.whole_meta()
+    assert meta["ok"], "set is not eligible for the whole-function kernel"
+    items = tabs.table(nat.TAB_WHOLE_ITEMS).astype(np.int64)
+    seo = tabs.table(nat.TAB_WHOLE_SEO).astype(np.int64)
+    m = tabs.m
+    TG = meta["threads"]
+    kk = np.arange(n1)[None, :]
+    buf = x.copy()
+    for h in range(m):
+        lst = items[meta["item_off"][h]: meta["item_off"][h] + meta["n_items"][h]]
+        assert len(lst) % TG == 0
+        t = (lst >> 16) & 63
+        lo = lst & 0xFFFF
+        lane = lst >> 22
+        live = t > 0
+        t, lo, lane = t[live], lo[live], lane[live]
+        valid = kk < t[:, None]
+        if h == 0:
+            idx = lo[:, None] + kk
+        else:
+            idx = seo[np.where(valid, lo[:, None] + kk, 0)] + lane[:, None]
+        flat = idx[valid]
+        assert len(np.unique(flat)) == len(flat) == len(x), "items do not cover every element exactly once"
         X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
         Y = apply_tri(X, M, mode)
         buf[idx[valid]] = Y[valid]
-        out[src] = buf
-    assert not np.isnan(out).any()
-    return out
+    return buf

@@ -149,11 +149,11 @@ def test_chebyshev_vs_oracle_larger(T):
         t.close()
 
 
-@pytest.mark.parametrize("whole", [2, 3, -2])
+@pytest.mark.parametrize("whole", [1, -2])
 @pytest.mark.parametrize("name", ["d3n7_cheb", "d2n8_cheb", "d2n6_inf_cheb", "d3n7_cheb_solve", "d3n6_inf", "c1_d2n10", "d3n12_p1", "d3n9_p05"])
 def test_whole_function_kernels_more_shapes(T, name, whole):
-    """The one-pass whole-function kernels (bulk-copy k_whole2, box-layout k_whole3) on upper-triangular
-    sweeps (Chebyshev), p = inf / 1 / 0.5 sets and m = 2; batched so that every CTA loops over several functions."""
+    """The one-pass whole-function kernel (k_whole, two thread groups per SM) on upper-triangular
+    sweeps (Chebyshev), p = inf / 1 / 0.5 sets and m = 2; batched so that every group loops over several functions."""
     g = load_case(name)
     t = make(T, g, exact_ifnt=True)
     if whole == -2:  # the slab kernel (coordinates 0 and 1 in one pass), forced on
@@ -384,24 +384,20 @@ def test_c5_dx_eval_vs_oracle(T):
 
 @pytest.mark.parametrize("opts", [
     {"use_whole": 0},
-    {"use_whole": 0, "use_tiles": 1},
-    {"use_whole": 0, "use_tiles": 1, "use_pipe": 1},
-    {"use_whole": 0, "use_tiles": 1, "l2_chunk_bytes": 200000},
-    {"use_whole": 0, "use_sorted": 1},
-    {"use_whole": 0, "use_groups": 0},
     {"use_whole": 1},
-    {"use_whole": 0, "use_planes": 1},
-    {"use_whole": 0, "use_two_lanes": 1},
-    {"use_whole": 2},
-    {"use_whole": 3},
+    {"use_whole": 1, "whole_threads": 384},
+    {"use_whole": 1, "whole_threads": 768, "whole_rows": 4},
+    {"use_whole": 1, "whole_threads": 384, "whole_order": 0, "whole_rows": 2},
+    {"use_whole": 1, "whole_order": 63},
     {"use_whole": 0, "use_slab": 2},
     {"use_whole": 0, "use_slab": 0},
+    {"use_whole": 0, "use_cta_cap": 0},
     {},
 ])
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d6n4", "d2n7_inf", "d3n12_solve", "c4_d3n30"])
 def test_alternative_kernel_families(T, name, opts):
-    """The selectable kernel families (row tiles, pipelined tiles, globally sorted, plain fibre order)
-    must all reproduce the reference bit for bit."""
+    """The selectable kernel paths (per-coordinate kernels, slab kernel, whole-function kernel
+    with 384 or 768 threads per CTA, 2- or 4-row blocks, other item orders) must all reproduce the reference bit for bit."""
     g = load_case(name)
     t = make(T, g, exact_ifnt=True)
     for k, v in opts.items():
@@ -535,13 +531,14 @@ def test_chebyshev_eval_fast_kernel_vs_oracle(T, m, n, p):
 
 @pytest.mark.parametrize("n,B", [(25, 1), (25, 16), (28, 9), (29, 300), (12, 7)])
 def test_whole_function_kernel_odd_sizes(T, n, B):
-    """k_whole2 with an odd number of coefficients: every second function starts 8 bytes off the 16-byte grid of the bulk
-    copies (the copy starts one element early) and the last function of a batch must not read past the end."""
+    """k_whole with an odd number of coefficients: every second function starts 8 bytes off the 16-byte grid of the
+    vectorised copies; one or two CTAs per SM, batches smaller and larger than the grid."""
     from oracle import oracle as O
 
     t = T(3, n, report=False, exact_ifnt=True)
     assert len(t) % 2 == 1
-    t.set_option("use_whole", 2)
+    t.set_option("use_whole", 1)
+    t.set_option("whole_threads", 384 if (n + B) % 2 else 768)
     o = O.OracleTransform(3, n, 2.0)
     rng = np.random.default_rng(n + B)
     v = rng.standard_normal((B, len(t)))

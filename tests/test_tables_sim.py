@@ -77,13 +77,19 @@ def test_index_rejects_bad_sets(built_lib):
         nat.IndexTables(B, 2)
 
 
-@pytest.mark.parametrize("name", ["c1_d2n10", "d3n12_p1", "d4n8", "d5n5_p1", "d6n4", "d3n6_inf", "d3n12_solve", "c2_d3n20_leja"])
-def test_emulated_tile_passes_match_reference(name, built_lib):
-    """Row-tile pass plan: (coordinate 1 + fused coordinate 0), then coordinates 2.. one pass each."""
+@pytest.mark.parametrize("threads", [384, 768])
+@pytest.mark.parametrize("name", ["c1_d2n10", "d3n12_p1", "d3n6_inf", "d3n12_solve", "c2_d3n20_leja", "c4_d3n30", "d2n10_solve"])
+def test_emulated_whole_function_kernel_matches_reference(name, threads, built_lib):
+    """k_whole from its real item tables (rounds of 384 or 768 items in thread order) -- bit-exact."""
     g = load_case(name)
     m, n = int(g["m"]), int(g["n"])
     n1 = n + 1
     tabs = nat.IndexTables(g["A"].astype(np.int64), n)
+    tabs.whole_build(threads=threads)
+    meta = tabs.whole_meta()
+    assert meta["ok"] and meta["threads"] == threads
+    if name == "c4_d3n30":
+        assert meta["max_items"] == 736 and meta["n_items"] == ([768] * 3)
     P = g["P"] if bool(g["colex"]) else None
     v = g["values"][0]
     x = v[P] if P is not None else v.copy()
@@ -91,11 +97,11 @@ def test_emulated_tile_passes_match_reference(name, built_lib):
         M, mode = U.unpack_lower(g["inv_Vx_lt"], n1), "lower"
     else:
         M, mode = U.unpack_lower(g["Vx_lt"], n1), "solve"
-    x = sim.sweep_tiles(x, tabs, 1, M, mode, n1, dim0=True)
-    for h in range(2, m):
-        x = sim.sweep_tiles(x, tabs, h, M, mode, n1, dim0=False)
-    assert np.array_equal(x, g["fnt"][0])
-    i = m - 1
-    D = U.unpack_upper(g["Dx_lt0"], n1)
-    if not np.isinf(float(g["p"])):
-        assert np.array_equal(sim.sweep_tiles(g["fnt"][0], tabs, i, D, "upper", n1, dim0=False), g[f"dx_{i}_1"])
+    assert np.array_equal(sim.whole_function(x, tabs, M, n1, mode), g["fnt"][0])
+    V = U.unpack_lower(g["Vx_lt"], n1)
+    y = sim.whole_function(g["fnt"][0], tabs, V, n1, "lower")
+    if P is not None:
+        z = np.empty_like(y)
+        z[P] = y
+        y = z
+    assert np.array_equal(y, g["ifnt"][0])
