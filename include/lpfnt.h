@@ -106,10 +106,12 @@ enum {
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);
 /* Item tables of the whole-function kernel (m = 2, 3; N < 65536).  lpfnt_index_whole_build re-builds them for CTAs of
- * `threads` threads (384: two CTAs per SM, 768: one) and an item order (2 bits per coordinate, 0 strict length order,
- * 1 / 2 classes of 8 / 16 rows, 3 natural; < 0 = default).  lpfnt_index_whole_meta fills 10 int32: ok, threads,
+ * `threads` threads (384 or 768), `fibres` (1 item per thread and round; 2: two of equal length class, folded side by side;
+ * 3: a long and a short one, folded one after the other) and an item order (2 bits per coordinate, 0 strict length order,
+ * 1 / 2 classes of 8 / 16 rows, 3 natural; + 64: chunks of 32 items dealt to the warps by a model of the shared FP64 pipe
+ * instead of the snake order over the four SM sub-partitions; < 0 = default).  lpfnt_index_whole_meta fills 10 int32: ok, threads,
  * longest item, most items of a list, {list offset, padded list length} per coordinate; returns the number written. */
-int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order);
+int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order, int fibres);
 int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta);
 int64_t lpfnt_index_size(const lpfnt_index *index, int what, int h);
 int lpfnt_index_copy(const lpfnt_index *index, int what, int h, void *dst);

@@ -40,7 +40,7 @@ def _declare(L):
     L.lpfnt_index_size.restype = i64
     L.lpfnt_index_size.argtypes = [vp, i32, i32]
     L.lpfnt_index_copy.argtypes = [vp, i32, i32, vp]
-    L.lpfnt_index_whole_build.argtypes = [vp, i32, i32]
+    L.lpfnt_index_whole_build.argtypes = [vp, i32, i32, i32]
     L.lpfnt_index_whole_meta.argtypes = [vp, vp]
     L.lpfnt_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.lpfnt_host_free.argtypes = [vp]
@@ -153,8 +153,8 @@ class IndexTables:
             check(lib().lpfnt_index_copy(self._h, what, h, out.ctypes.data))
         return out.reshape(-1, 2) if what in (TAB_FIB_ENT, TAB_GROUPS) else out
 
-    def whole_build(self, threads: int = 768, order: int = -1):
-        check(lib().lpfnt_index_whole_build(self._h, int(threads), int(order)))
+    def whole_build(self, threads: int = 768, order: int = -1, fibres: int = 1):
+        check(lib().lpfnt_index_whole_build(self._h, int(threads), int(order), int(fibres)))
 
     def whole_meta(self) -> dict:
         meta = np.zeros(10, dtype=np.int32)

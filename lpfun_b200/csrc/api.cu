@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <bitset>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -81,17 +82,19 @@ struct lpfnt_plan {
     int64_t launches = 0;
     int64_t table_bytes = 0;
     int force_generic = 0;
-    // whole-function kernel (m = 2, 3): tables of HostIndex::whole on the device
+    // whole-function kernel (m = 2, 3): tables of HostIndex::whole on the device, one set for the exact forms
+    // (index 0) and one for the fused-multiply-add forms (index 1): their best CTA shapes differ
     struct Whole {
         WholeHost h;                         // host copy (items / seo dropped after the upload)
         uint32_t *d_items = nullptr;
-        uint16_t *d_seo = nullptr, *d_perm16 = nullptr;
+        uint16_t *d_seo = nullptr;
         int32_t total_items = 0, seo_len = 0;
         size_t smem_bytes = 0;
-        uint64_t attr_set = 0;               // bit per kernel instantiation: dynamic shared memory opted in on this device
-    } whole;
+    } whole[2];
+    struct WholeCfg { int threads = -1, fibres = -1, order = kWholeDefaultOrder, rows = -1; } wcfg[2];
+    uint16_t *d_perm16 = nullptr;
+    std::bitset<512> whole_attr_set;         // per kernel instantiation: dynamic shared memory opted in on this device
     int use_whole = -1;                      // -1 auto (batches of >= 8 functions), 0 off, 1 always
-    int whole_threads = -1, whole_order = kWholeDefaultOrder, whole_rows = -1;
     HostIndex *hx = nullptr;                 // kept for plans that can run the whole-function kernel (re-build of its tables)
     // slab kernel (coordinates 0 and 1 in one pass, any m >= 2; see k_slab)
     struct Slabs {
@@ -373,29 +376,40 @@ int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
 }
 
 // ---- whole-function kernel (k_whole): tables, eligibility, launch ----
-void free_whole(lpfnt_plan *p) {
-    lpfnt_plan::Whole &W = p->whole;
+void free_whole(lpfnt_plan *p, int which) {
+    lpfnt_plan::Whole &W = p->whole[which];
     cudaFree(W.d_items); cudaFree(W.d_seo);
     W.d_items = nullptr; W.d_seo = nullptr;
     W.h = WholeHost();
 }
 
-int upload_whole(lpfnt_plan *p) {
-    lpfnt_plan::Whole &W = p->whole;
-    free_whole(p);
+// CTA shape: two CTAs of 384 threads (one fibre per thread) per SM when two functions (plus tables) fit into shared memory;
+// else one CTA per SM: the fused forms with 384 threads and TWO fibres each, folded side by side (every matrix entry feeds
+// two DFMA: the constant path, one LDCU.64 per ~4 cycles and SM sub-partition, is half as loaded: ifnt 0.53 -> 0.49 ms at
+// d = 3, n = 30, B = 4096), the exact forms with 768 threads and one fibre each.  Measured alternative for the exact
+// forms (fibres = 3): 384 threads with a long and a short item each, one after the other -- equal work per warp and
+// interleaved row chains bring the triangle phases to 88 % of the FP64 pipe (7.3 K cycles per sweep instead of 8.5-10 K),
+// but the load / store phases of 12 instead of 24 warps grow by more (0.69 vs 0.61 ms).
+int upload_whole(lpfnt_plan *p, int which) {
+    lpfnt_plan::Whole &W = p->whole[which];
+    const lpfnt_plan::WholeCfg &cfg = p->wcfg[which];
+    free_whole(p, which);
     if (!p->hx) return LPFNT_OK;
-    // two CTAs of 384 threads per SM when two functions (plus tables) fit into shared memory, else one CTA of 768
-    int threads = p->whole_threads;
     for (int pass = 0; pass < 2; ++pass) {
-        const int tg = threads > 0 ? threads : (pass == 0 ? 384 : 768);
-        p->hx->build_whole(tg, p->whole_order);
+        int tg = cfg.threads, nf = cfg.fibres;
+        if (pass == 0) { if (tg <= 0) tg = 384; if (nf <= 0) nf = 1; }
+        else { if (nf <= 0) nf = (tg == 768) ? 1 : (tg == 384 ? (which == 1 ? 2 : 3) : (which == 1 ? 2 : 1)); if (tg <= 0) tg = nf == 1 ? 768 : 384; }
+        if (nf >= 2) tg = 384;  // two fibres per thread: 168 registers, i.e. 384 threads
+        p->hx->build_whole(tg, cfg.order, nf);
         const WholeHost &h = p->hx->whole;
         if (!h.ok) return LPFNT_OK;
         W.smem_bytes = whole_smem_bytes(int(p->N), int(h.items.size()), int(h.seo.size()), p->has_perm);
-        if (threads > 0 || W.smem_bytes <= size_t(kWholeSmemPerCta) || pass == 1) break;
+        const bool explicit_shape = cfg.threads > 0 && cfg.fibres > 0;
+        if (explicit_shape || pass == 1 || (tg == 384 && nf == 1 && W.smem_bytes <= size_t(kWholeSmemPerCta))) break;
     }
     W.h = p->hx->whole;
-    if (W.smem_bytes > size_t(W.h.threads == 384 ? kWholeSmemPerCta : kWholeSmemLimit)) { W.h = WholeHost(); return LPFNT_OK; }
+    const bool two_ctas = W.h.threads == 384 && W.h.fibres == 1 && W.smem_bytes <= size_t(kWholeSmemPerCta);
+    if (W.smem_bytes > size_t(two_ctas ? kWholeSmemPerCta : kWholeSmemLimit)) { W.h = WholeHost(); return LPFNT_OK; }
     int rc;
     if ((rc = upload(&W.d_items, W.h.items.data(), W.h.items.size(), p))) return rc;
     if ((rc = upload(&W.d_seo, W.h.seo.data(), W.h.seo.size(), p))) return rc;
@@ -407,7 +421,7 @@ int upload_whole(lpfnt_plan *p) {
 }
 
 bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, int64_t batch) {
-    const lpfnt_plan::Whole &W = p->whole;
+    const lpfnt_plan::Whole &W = p->whole[spec.fma ? 1 : 0];
     if (!W.h.ok || p->force_generic || int(dims.size()) != p->m) return false;
     // automatic: enough functions to fill a few SMs (a single function would run on ONE SM) and enough items to keep
     // most of a CTA busy
@@ -415,45 +429,48 @@ bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int>
     if (!want) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
     if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
+    if (W.h.fibres == 2 && !W.h.seq && sweep_mode(spec) != kLowerMatvec) return false;  // two fibres side by side: lower mat-vec only
     if (reinterpret_cast<uintptr_t>(in) & 15) return false;    // bulk copies need a 16-byte aligned batch
     return true;
 }
 
 int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
-    lpfnt_plan::Whole &W = p->whole;
+    const int which = spec.fma ? 1 : 0;
+    lpfnt_plan::Whole &W = p->whole[which];
     const int mode = sweep_mode(spec);
     const int cap = pick_cap(std::max(W.h.max_t, 1));
     const double *tri = operator_tri(p, spec.op, cap);
     WholeArgs a{};
-    a.items = W.d_items; a.seo = W.d_seo; a.perm16 = W.d_perm16;
+    a.items = W.d_items; a.seo = W.d_seo; a.perm16 = p->d_perm16;
     a.total_items = W.total_items; a.seo_len = W.seo_len;
     for (int h = 0; h < 3; ++h) { a.item_off[h] = W.h.item_off[h]; a.n_items[h] = W.h.n_items[h]; }
     a.gather = gather ? 1 : 0; a.scatter = scatter ? 1 : 0;
     a.n_elem = int32_t(p->N); a.m = p->m;
     a.dbg = p->d_timeline;
     const bool timeline = p->d_timeline != nullptr;
-    // rows folded side by side: 4 for the fused form (its chains are latency bound: 56 -> 75 % of the FP64 pipe at 12
-    // warps per SM, tools/probe4.cu), 2 for the exact form (twice the instructions per term already)
-    const int rows = p->whole_rows > 0 ? p->whole_rows : (spec.fma ? 4 : 2);
-    const int key = ((cap / 8 - 1) * 5 + (mode == kLowerMatvec ? (spec.fma ? 1 : 0) : mode == kUpperMatvec ? (spec.fma ? 3 : 2) : 4)) * 3 +
-                    (W.h.threads == 384 ? 0 : 1) + (rows == 4 ? 1 : 0) * 0;  // < 64
-    const int key2 = key + (rows == 4 ? 60 : 0);
-    const bool set_attr = timeline || key2 >= 64 || !(W.attr_set >> key2 & 1u);
+    // rows folded side by side (one fibre per thread): 4 for the fused form (its chains are latency bound), 2 for the
+    // exact form (twice the instructions per term already)
+    const int rows = W.h.fibres == 2 ? 2 : (p->wcfg[which].rows > 0 ? p->wcfg[which].rows : (spec.fma ? 4 : 2));
+    const int modekind = mode == kLowerMatvec ? (spec.fma ? 1 : 0) : mode == kUpperMatvec ? (spec.fma ? 3 : 2) : 4;
+    const int shape = (W.h.threads == 384 ? 0 : 1) + (W.h.fibres == 2 ? (W.h.seq ? 6 : 2) : (rows == 4 ? 4 : 0));  // < 8
+    const int key = ((cap / 8 - 1) * 5 + modekind) * 8 + shape + (timeline ? 160 : 0);                               // < 320
+    const int fibres_code = W.h.fibres == 2 ? (W.h.seq ? 3 : 2) : 1;
+    const bool set_attr = !p->whole_attr_set[key];
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
         a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
-        const int per_sm = W.h.threads == 384 ? 2 : 1;
+        const int per_sm = (W.h.threads == 384 && W.h.fibres == 1 && W.smem_bytes <= size_t(kWholeSmemPerCta)) ? 2 : 1;
         const int grid = int(std::min<int64_t>(nb, int64_t(per_sm) * p->num_sms));
         cudaError_t e = cudaSuccess;
         trace_begin(p, 1400, s);
-        LAUNCH_CAP(cap, launch_whole<8>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
-                   launch_whole<16>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
-                   launch_whole<24>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
-                   launch_whole<32>(mode, spec.fma, W.h.threads, rows, timeline, a, tri, grid, W.smem_bytes, set_attr, s))
+        LAUNCH_CAP(cap, launch_whole<8>(mode, spec.fma, W.h.threads, rows, fibres_code, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
+                   launch_whole<16>(mode, spec.fma, W.h.threads, rows, fibres_code, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
+                   launch_whole<24>(mode, spec.fma, W.h.threads, rows, fibres_code, timeline, a, tri, grid, W.smem_bytes, set_attr, s),
+                   launch_whole<32>(mode, spec.fma, W.h.threads, rows, fibres_code, timeline, a, tri, grid, W.smem_bytes, set_attr, s))
         trace_end(p, s);
         p->launches += 1;
         if (e != cudaSuccess) { set_error(std::string("whole-function kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
-        if (!timeline && key2 < 64) W.attr_set |= uint64_t(1) << key2;
+        p->whole_attr_set[key] = true;
     }
     return LPFNT_OK;
 }
@@ -668,9 +685,10 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if (perm) {
             std::vector<uint16_t> p16(N);
             for (int64_t i = 0; i < N; ++i) p16[i] = uint16_t(perm[i]);
-            if ((rc = upload(&p->whole.d_perm16, p16.data(), p16.size(), p))) return fail(rc);
+            if ((rc = upload(&p->d_perm16, p16.data(), p16.size(), p))) return fail(rc);
         }
-        if ((rc = upload_whole(p))) return fail(rc);
+        for (int which = 0; which < 2; ++which)
+            if ((rc = upload_whole(p, which))) return fail(rc);
     }
     if (!hx.eval_block.empty()) {
         static_assert(sizeof(EvalBlock) == sizeof(int4), "EvalBlock must match int4");
@@ -703,8 +721,9 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
-    free_whole(p);
-    cudaFree(p->whole.d_perm16);
+    free_whole(p, 0);
+    free_whole(p, 1);
+    cudaFree(p->d_perm16);
     delete p->hx;
     cudaFree(p->d_timeline);
     cudaFree(p->slabs.d_desc); cudaFree(p->slabs.d_item0); cudaFree(p->slabs.d_item1);
@@ -753,13 +772,26 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
         return LPFNT_OK;
     }
     if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
-    if (std::strcmp(name, "whole_rows") == 0) { p->whole_rows = (value == 2 || value == 4) ? int(value) : -1; return LPFNT_OK; }
-    if (std::strcmp(name, "whole_threads") == 0 || std::strcmp(name, "whole_order") == 0) {
-        if (name[6] == 't') p->whole_threads = (value == 384 || value == 768) ? int(value) : -1;
-        else p->whole_order = value < 0 ? kWholeDefaultOrder : int(value & 63);
-        CK(cudaSetDevice(p->device));
-        CK(cudaDeviceSynchronize());  // the tables may be in use
-        return upload_whole(p);
+    if (std::strncmp(name, "whole_", 6) == 0) {
+        // whole_<threads|fibres|order|rows>[_exact|_fma]: CTA shape of the whole-function kernel, for both forms or one
+        std::string key(name + 6);
+        int lo = 0, hi = 1;
+        if (key.size() > 6 && key.compare(key.size() - 6, 6, "_exact") == 0) { hi = 0; key.resize(key.size() - 6); }
+        else if (key.size() > 4 && key.compare(key.size() - 4, 4, "_fma") == 0) { lo = 1; key.resize(key.size() - 4); }
+        if (key == "threads" || key == "fibres" || key == "order" || key == "rows") {
+            for (int w = lo; w <= hi; ++w) {
+                lpfnt_plan::WholeCfg &c = p->wcfg[w];
+                if (key == "threads") c.threads = (value == 384 || value == 768) ? int(value) : -1;
+                else if (key == "fibres") c.fibres = (value >= 1 && value <= 3) ? int(value) : -1;
+                else if (key == "order") c.order = value < 0 ? kWholeDefaultOrder : int(value & 127);
+                else c.rows = (value == 2 || value == 4) ? int(value) : -1;
+            }
+            if (key == "rows") return LPFNT_OK;
+            CK(cudaSetDevice(p->device));
+            CK(cudaDeviceSynchronize());  // the tables may be in use
+            for (int w = lo; w <= hi; ++w) { int rc = upload_whole(p, w); if (rc) return rc; }
+            return LPFNT_OK;
+        }
     }
     set_error(std::string("unknown option: ") + name);
     return LPFNT_EINVAL;

@@ -343,26 +343,39 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
     if (n <= 255 && m >= 2) {
         line_last.resize(size_t(N1));
         for (int64_t l = 0; l < N1; ++l) line_last[l] = static_cast<uint8_t>(key(l, m - 1));
-        build_whole(768, kWholeDefaultOrder);
+        build_whole(768, kWholeDefaultOrder, 1);
     }
     return true;
 }
 
-void HostIndex::build_whole(int threads, int order) {
+void HostIndex::build_whole(int threads, int order, int fibres) {
     whole = WholeHost();
     WholeHost &W = whole;
-    if (m < 2 || m > 3 || N >= 65536 || max_line > kMaxRegT || (threads != 384 && threads != 768)) return;
+    if (m < 2 || m > 3 || N >= 65536 || max_line > kMaxRegT || (threads != 384 && threads != 768) || fibres < 1 || fibres > 3) return;
     for (int h = 1; h < m; ++h)
         if (dims[h].max_lines > kMaxRegT) return;
-    const int TG = threads;
+    // fibres: 1, 2 (two items of the same length class per thread, folded side by side) or 3 (two items per thread folded
+    // one after the other: a long and a short one)
+    const bool seq = fibres == 3;
+    const int TG = threads, NF = fibres == 1 ? 1 : 2, RT = TG * NF;  // a round = RT items: thread i owns slots i, TG + i, ...
     W.threads = threads;
-    auto rounds = [&](int64_t items) { return int32_t((items + TG - 1) / TG) * TG; };
-    // seo: per coordinate h >= 1 the line offsets in fibre order
-    std::vector<int32_t> seo_off(m, 0);
+    W.fibres = NF;
+    W.seq = seq;
+    auto rounds = [&](int64_t items) { return int32_t((items + RT - 1) / RT) * RT; };
+    // seo: per coordinate h >= 1 the line offsets in fibre order; every fibre's list starts on a multiple of four entries
+    // (8 bytes: the kernel fetches four offsets per load) and the table ends with a full row of padding (the kernel reads
+    // whole groups of four / eight entries, also past a short fibre's end)
+    std::vector<std::vector<int32_t>> seo_start(m);
     for (int h = 1; h < m; ++h) {
-        seo_off[h] = int32_t(W.seo.size());
-        for (const FibEnt &en : dims[h].ent) W.seo.push_back(uint16_t(en.off));
+        const DimTable &D = dims[h];
+        seo_start[h].resize(D.num_fibres);
+        for (int32_t f = 0; f < D.num_fibres; ++f) {
+            while (W.seo.size() % 4) W.seo.push_back(0);
+            seo_start[h][f] = int32_t(W.seo.size());
+            for (int32_t r = D.fib_ptr[f]; r < D.fib_ptr[f + 1]; ++r) W.seo.push_back(uint16_t(D.ent[r].off));
+        }
     }
+    for (int q = 0; q < kMaxRegT + 8 || W.seo.size() % 8; ++q) W.seo.push_back(0);
     if (W.seo.size() > 65536) return;
     struct Item { int t; uint32_t w; };
     for (int h = 0; h < m; ++h) {
@@ -380,7 +393,7 @@ void HostIndex::build_whole(int threads, int order) {
                 for (int32_t lane = 0; lane < lanes; ++lane) {
                     int32_t t = 0;
                     while (t < nl && D.ent[p0 + t].len > lane) ++t;
-                    nat.push_back({t, uint32_t(seo_off[h] + p0) | (uint32_t(t) << 16) | (uint32_t(lane) << 22)});
+                    nat.push_back({t, uint32_t(seo_start[h][f]) | (uint32_t(t) << 16) | (uint32_t(lane) << 22)});
                 }
             }
         }
@@ -392,13 +405,64 @@ void HostIndex::build_whole(int threads, int order) {
         W.item_off[h] = int32_t(W.items.size());
         W.n_items[h] = padded;
         W.max_items = std::max(W.max_items, nit);
-        for (int32_t r0 = 0; r0 < padded; r0 += TG) {
-            for (int tid = 0; tid < TG; ++tid) {
-                // chunks of 32 items (longest first) are dealt to the warps in SNAKE order over the four SM sub-partitions
-                // (warp w runs on sub-partition w % 4): 0 1 2 3 / 3 2 1 0 / ...
-                const int w = tid >> 5, grp = w >> 2;
-                const int chunk = grp * 4 + ((grp & 1) ? 3 - (w & 3) : (w & 3));
-                const int32_t src = r0 + chunk * 32 + (tid & 31);
+        const int nw = TG / 32, CH = seq ? 32 : 32 * NF;
+        for (int32_t r0 = 0; r0 < padded; r0 += RT) {
+            // chunks of CH items (longest first); warp w runs on SM sub-partition w % 4
+            const int nch = RT / CH;
+            std::vector<double> wgt(nch, 0.0);
+            for (int c = 0; c < nch; ++c) {
+                int tm = 0;
+                for (int i = 0; i < CH; ++i) { const int32_t src = r0 + c * CH + i; if (src < nit) tm = std::max(tm, nat[src].t); }
+                const int tt = (tm + 1) & ~1;
+                wgt[c] = 0.5 * tt * (tt + 1);
+            }
+            // a warp's unit of work: one chunk, or (seq) the LONG chunk c together with the SHORT chunk nch - 1 - c -- the
+            // work of an item is quadratic in its length, so the sums come out nearly equal
+            std::vector<double> unit(nw, 0.0);
+            for (int c = 0; c < nw; ++c) unit[c] = seq ? wgt[c] + wgt[nch - 1 - c] : wgt[c];
+            std::vector<int> warp_of(nw);  // unit -> warp
+            // start: SNAKE order over the four sub-partitions (0 1 2 3 / 3 2 1 0 / ...): equal sums of work
+            for (int c = 0; c < nw; ++c) { const int grp = c >> 2; warp_of[c] = grp * 4 + ((grp & 1) ? 3 - (c & 3) : (c & 3)); }
+            if (order & 64) {
+                // The FP64 pipe of a sub-partition is shared by its warps, and one or two warps alone cannot keep it busy
+                // (tools/probe5.cu: equal sums but unequal chunks cost 17-25 % of a sweep): the sweep ends when the
+                // sub-partition whose longest unit outlasts its other units by most is done.  Model: processor sharing
+                // with rate r(j) of the pipe while j warps are still computing; hill-climb over swaps.
+                const double r1 = NF == 2 ? 0.70 : 0.45, r2 = NF == 2 ? 0.88 : 0.75, r3 = NF == 2 ? 0.93 : 0.90, r4 = 0.93;
+                auto part_time = [&](int sp) {
+                    double a[64]; int k = 0;
+                    for (int c = 0; c < nw; ++c) if ((warp_of[c] & 3) == sp && unit[c] > 0) a[k++] = unit[c];
+                    std::sort(a, a + k);  // ascending: a[0] finishes first
+                    double tsum = 0, prev = 0;
+                    for (int i = 0; i < k; ++i) {
+                        const int act = k - i;
+                        const double r = act == 1 ? r1 : act == 2 ? r2 : act == 3 ? r3 : r4;
+                        tsum += (a[i] - prev) * act / r;
+                        prev = a[i];
+                    }
+                    return tsum;
+                };
+                auto cost = [&]() { double mx = 0, sm = 0; for (int sp = 0; sp < 4; ++sp) { const double t = part_time(sp); mx = std::max(mx, t); sm += t; } return mx + 1e-3 * sm; };
+                double best = cost();
+                for (bool improved = true; improved;) {
+                    improved = false;
+                    for (int c1 = 0; c1 < nw; ++c1)
+                        for (int c2 = c1 + 1; c2 < nw; ++c2) {
+                            if ((warp_of[c1] & 3) == (warp_of[c2] & 3)) continue;
+                            std::swap(warp_of[c1], warp_of[c2]);
+                            const double t = cost();
+                            if (t < best - 1e-9) { best = t; improved = true; }
+                            else std::swap(warp_of[c1], warp_of[c2]);
+                        }
+                }
+            }
+            std::vector<int> unit_of(nw);
+            for (int c = 0; c < nw; ++c) unit_of[warp_of[c]] = c;
+            for (int slot = 0; slot < RT; ++slot) {
+                // side by side: lane l of the warp owns items l and 32 + l of its chunk (neighbours in the length order)
+                const int f = slot / TG, tid = slot % TG;
+                const int u = unit_of[tid >> 5];
+                const int32_t src = seq ? r0 + (f == 0 ? u : nch - 1 - u) * 32 + (tid & 31) : r0 + u * CH + f * 32 + (tid & 31);
                 W.items.push_back(src < nit ? nat[src].w : 0u);
             }
         }
@@ -523,10 +587,11 @@ int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **
     return LPFNT_OK;
 }
 int lpfnt_index_destroy(lpfnt_index *index) { delete index; return LPFNT_OK; }
-int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order) {
+int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order, int fibres) {
     if (!index) { set_error("index is null"); return LPFNT_EINVAL; }
     if (threads != 384 && threads != 768) { set_error("whole_build: threads must be 384 or 768"); return LPFNT_EINVAL; }
-    index->hx.build_whole(threads, order < 0 ? kWholeDefaultOrder : order);
+    if (fibres < 1 || fibres > 3) { set_error("whole_build: fibres must be 1, 2 (two per thread, side by side) or 3 (two per thread, one after the other)"); return LPFNT_EINVAL; }
+    index->hx.build_whole(threads, order < 0 ? kWholeDefaultOrder : order, fibres);
     return LPFNT_OK;
 }
 int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta) {

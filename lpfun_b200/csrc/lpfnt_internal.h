@@ -56,7 +56,9 @@ struct DimTable {
 // to the warps in snake order over the four SM sub-partitions.  Empty slots are 0 (t = 0).
 struct WholeHost {
     bool ok = false;
-    int threads = 0;                       // threads per CTA the lists were laid out for (384: two CTAs per SM, 768: one)
+    int threads = 0;                       // threads per CTA the lists were laid out for (384 or 768)
+    int fibres = 1;                        // items per thread and round
+    bool seq = false;                      // two items per thread: false = folded side by side, true = one after the other
     int32_t item_off[3] = {0, 0, 0}, n_items[3] = {0, 0, 0};
     int32_t max_t = 0, max_items = 0;
     std::vector<uint32_t> items;
@@ -80,10 +82,11 @@ struct HostIndex {
     std::vector<uint8_t> line_alpha;     // N_1 * (m-1): (a_1..a_{m-1}) of every line, for eval (n <= 255)
     // returns false (and sets the error) if A is not a colex-ordered downward-closed set
     bool build(const int64_t *A, int64_t N, int m, int n);
-    // (re)build `whole` for CTAs of `threads` threads (384 or 768); order = 2 bits per coordinate: 0 strict length order,
-    // 1 / 2 length classes of 8 / 16 (natural order inside a class), 3 natural
-    void build_whole(int threads, int order);
+    // (re)build `whole` for CTAs of `threads` threads (384 or 768) owning `fibres` items each per round; order = 2 bits per coordinate: 0 strict length order,
+    // 1 / 2 length classes of 8 / 16 (natural order inside a class), 3 natural; bit 6: chunks dealt to the warps by the
+    // pipe-sharing model instead of the snake order
+    void build_whole(int threads, int order, int fibres);
 };
-constexpr int kWholeDefaultOrder = 0 | (2 << 2) | (2 << 4);
+constexpr int kWholeDefaultOrder = 0 | (2 << 2) | (2 << 4) | 64;
 
 }  // namespace lpfnt

@@ -26,9 +26,9 @@ cudaError_t group_launch(const GroupSweepArgs &a, const PackedTri<T> &M, int bat
     return cudaGetLastError();
 }
 
-template <int MODE, bool FMA, int TG, int ROWS, bool TL = false>
+template <int MODE, bool FMA, int TG, int ROWS, int NF = 1, bool SEQ = false, int MINB = 1, bool TL = false>
 cudaError_t whole_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, size_t smem, bool set_attr, cudaStream_t s) {
-    auto kern = k_whole<T, MODE, FMA, TG, ROWS, TL>;
+    auto kern = k_whole<T, MODE, FMA, TG, ROWS, NF, SEQ, MINB, TL>;
     if (set_attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
@@ -36,21 +36,44 @@ cudaError_t whole_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, si
     kern<<<grid, TG, smem, s>>>(a, M);
     return cudaGetLastError();
 }
+// one fibre per thread: 768 threads, or 384 with the register budget of two CTAs per SM
 template <int MODE, bool FMA, int ROWS>
 cudaError_t whole_launch_tg(int threads, bool timeline, const WholeArgs &a, const PackedTri<T> &M, int grid, size_t smem, bool set_attr, cudaStream_t s) {
 #if LPFNT_MAXT == 32
     if (timeline && MODE == kLowerMatvec)
-        return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS, true>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS, true>(a, M, grid, smem, set_attr, s);
+        return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS, 1, false, 2, true>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS, 1, false, 1, true>(a, M, grid, smem, set_attr, s);
 #endif
-    return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS>(a, M, grid, smem, set_attr, s);
+    return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS, 1, false, 2>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS>(a, M, grid, smem, set_attr, s);
+}
+// two fibres per thread, 384 threads, one CTA per SM: side by side (lower mat-vec) or one after the other (any mode)
+template <int MODE, bool FMA, bool SEQ>
+cudaError_t whole_launch_two(bool timeline, const WholeArgs &a, const PackedTri<T> &M, int grid, size_t smem, bool set_attr, cudaStream_t s) {
+#if LPFNT_MAXT == 32
+    if (timeline && MODE == kLowerMatvec) return whole_launch<MODE, FMA, 384, 2, 2, SEQ, 1, true>(a, M, grid, smem, set_attr, s);
+#endif
+    return whole_launch<MODE, FMA, 384, 2, 2, SEQ, 1>(a, M, grid, smem, set_attr, s);
 }
 }  // namespace
 
+// fibres: 1; 2 = two per thread side by side; 3 = two per thread one after the other
 template <>
-cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, bool timeline, const WholeArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s) {
+cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibres, bool timeline, const WholeArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s) {
     PackedTri<T> M;
     std::memcpy(M.v, tri, sizeof(M.v));
     if (threads != 384 && threads != 768) return cudaErrorInvalidValue;
+    if (fibres == 2) {
+        if (mode != kLowerMatvec || threads != 384) return cudaErrorInvalidValue;
+        return fma ? whole_launch_two<kLowerMatvec, true, false>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, false>(timeline, a, M, grid, smem, set_attr, s);
+    }
+    if (fibres == 3) {
+        if (threads != 384) return cudaErrorInvalidValue;
+        switch (mode) {
+            case kLowerMatvec: return fma ? whole_launch_two<kLowerMatvec, true, true>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, true>(timeline, a, M, grid, smem, set_attr, s);
+            case kUpperMatvec: return fma ? whole_launch_two<kUpperMatvec, true, true>(false, a, M, grid, smem, set_attr, s) : whole_launch_two<kUpperMatvec, false, true>(false, a, M, grid, smem, set_attr, s);
+            case kLowerSolve: return whole_launch_two<kLowerSolve, false, true>(false, a, M, grid, smem, set_attr, s);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     // 4-row blocks exist for the lower mat-vec (fnt / ifnt); every other mode folds two rows
     switch (mode) {
         case kLowerMatvec:

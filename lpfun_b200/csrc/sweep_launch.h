@@ -18,11 +18,11 @@ cudaError_t launch_group_sweep(int mode, bool fma, const GroupSweepArgs &a, cons
 // slab kernel: coordinates 0 and 1 in one pass (any m >= 2)
 template <int MAXT>
 cudaError_t launch_slab(int mode, bool fma, const SlabArgs &a, const double *tri, int grid, cudaStream_t s);
-// whole-function kernel (m = 2, 3): threads = 384 (two CTAs per SM) or 768 (one); rows = 2 or 4 output rows folded side by
-// side; timeline: the instantiation with clock64 stamps (MAXT = 32, lower mat-vec only).
+// whole-function kernel (m = 2, 3): threads = 384 or 768; rows = 2 or 4 output rows folded side by side; fibres = 1 or 2
+// items per thread (2: lower mat-vec, 384 threads); timeline: the instantiation with clock64 stamps (MAXT = 32, lower mat-vec only).
 // set_attr: opt in to `smem` bytes of dynamic shared memory first (per device and kernel, tracked by the plan).
 template <int MAXT>
-cudaError_t launch_whole(int mode, bool fma, int threads, int rows, bool timeline, const WholeArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s);
+cudaError_t launch_whole(int mode, bool fma, int threads, int rows, int fibres, bool timeline, const WholeArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s);
 
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
 cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int batch, bool restrict_, cudaStream_t s);

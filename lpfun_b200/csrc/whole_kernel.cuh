@@ -89,8 +89,45 @@ inline size_t whole_smem_bytes(int n_elem, int total_items, int seo_len, bool pe
     return size_t((n_elem + 3) & ~1) * 8 + 16 + size_t(total_items) * 4 + size_t((seo_len + 7) & ~7) * 2 + (perm ? size_t((n_elem + 7) & ~7) * 2 : 0);
 }
 
-template <int MAXT, int MODE, bool FMA, int TG, int ROWS, bool TL = false>
-__global__ void __launch_bounds__(TG, TG <= 384 ? 2 : 1) k_whole(const __grid_constant__ WholeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+// Two fibres per thread, sharing every matrix entry (lower mat-vec, rows k and k-1 of both fibres side by side: four
+// independent chains per thread).  The constant path delivers one LDCU.128 (two entries) per ~8 cycles and SM
+// sub-partition (tools/probe5.cu): enough for the exact form of ONE fibre (2 DMUL + 2 DADD = 8 pipe cycles per two
+// entries), half of what the fused form needs (2 DFMA = 4 cycles) -- with two fibres per thread every entry feeds twice the
+// arithmetic.  tg: warp maximum of both lengths.
+template <int MAXT, bool FMA>
+__device__ __forceinline__ void apply_fibre2(double (&x)[MAXT], double (&y)[MAXT], const PackedTri<MAXT> &M, const int tg) {
+    static_assert(MAXT % 2 == 0, "rows are processed in pairs");
+#pragma unroll
+    for (int k = MAXT - 1; k >= 1; k -= 2) {
+        if (k - 1 < tg) {
+            double a1 = 0.0, a0 = 0.0, b1 = 0.0, b0 = 0.0;
+#pragma unroll
+            for (int j = 0; j < k; ++j) {
+                const double m1 = M.v[k * (k + 1) / 2 + j], m0 = M.v[(k - 1) * k / 2 + j];
+                a1 = mac<FMA>(a1, m1, x[j]);
+                b1 = mac<FMA>(b1, m1, y[j]);
+                a0 = mac<FMA>(a0, m0, x[j]);
+                b0 = mac<FMA>(b0, m0, y[j]);
+            }
+            const double md = M.v[k * (k + 1) / 2 + k];
+            x[k] = mac<FMA>(a1, md, x[k]);
+            y[k] = mac<FMA>(b1, md, y[k]);
+            x[k - 1] = a0;
+            y[k - 1] = b0;
+        }
+    }
+}
+
+// NF = fibres per thread: 1 or 2 (the item lists then hold rounds of 2 * TG items, thread i owning slots i and TG + i).
+// SEQ = false: the two fibres are folded side by side and share every matrix entry (lower mat-vec; two items of the same
+// length class: the fused forms, whose constant path is the limit).  SEQ = true: one after the other, each with its own
+// warp-uniform row bound -- the host pairs a LONG with a SHORT chunk of items per warp, so that all warps carry the same
+// work (work is quadratic in the length: rank r + rank 23 - r is constant within 6 % at d = 3, n = 30), and the 168
+// registers of a 384-thread CTA let ptxas keep the two row chains of the exact form interleaved (at the 80 registers of
+// a 768-thread CTA it emits ONE serial DMUL -> DADD chain per warp: half the rate once a warp runs alone).
+// MINB: CTAs per SM the register budget is cut for.
+template <int MAXT, int MODE, bool FMA, int TG, int ROWS, int NF = 1, bool SEQ = false, int MINB = 1, bool TL = false>
+__global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ WholeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *const buf0 = reinterpret_cast<double *>(smem_raw);  // 16-byte aligned landing zone
 #define W_NPAD ((a.n_elem + 3) & ~1)
@@ -117,7 +154,7 @@ __global__ void __launch_bounds__(TG, TG <= 384 ? 2 : 1) k_whole(const __grid_co
     // colex gather of the input: by the coordinate-0 loads (every thread reads its line through the permutation, then a
     // barrier, then everybody writes) when coordinate 0 is ONE round; with several rounds that would race, and the
     // permutation is applied by cp.async while the function is fetched instead
-    const bool gather_cp = a.gather && a.n_items[0] > TG;
+    const bool gather_cp = a.gather && a.n_items[0] > TG * NF;
     const bool oddN = (N & 1) != 0;
 
     // Bulk copies move 16-byte granules between 16-byte aligned addresses.  For odd N every second function starts 8
@@ -172,54 +209,102 @@ __global__ void __launch_bounds__(TG, TG <= 384 ? 2 : 1) k_whole(const __grid_co
         for (int h = 0; h < a.m; ++h) {
             const bool last = (h == a.m - 1);
 #pragma unroll 1
-            for (int r0 = 0; r0 < a.n_items[h]; r0 += TG) {
-                double x[MAXT];
-                int t;
+            for (int r0 = 0; r0 < a.n_items[h]; r0 += TG * NF) {
+                static_assert(NF == 1 || (NF == 2 && (SEQ || MODE == kLowerMatvec)), "two fibres side by side: lower mat-vec only");
+                double x[NF][MAXT];
+                int tmax = 0, tf[NF];
                 {
                     double *buf = buf0 + ((oddN && !gather_cp) ? (b & 1) : 0);
-                    const uint32_t it = W_SITEM[a.item_off[h] + r0 + threadIdx.x];
-                    t = int((it >> 16) & 63u);
-                    if (h == 0 && a.gather && !gather_cp) {
-                        const uint16_t *sp = W_SPERM + (it & 0xffffu);
+                    uint32_t it[NF];
 #pragma unroll
-                        for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? buf[sp[k]] : 0.0;
+                    for (int f = 0; f < NF; ++f) {
+                        it[f] = W_SITEM[a.item_off[h] + r0 + f * TG + threadIdx.x];
+                        tf[f] = int((it[f] >> 16) & 63u);
+                        tmax = max(tmax, tf[f]);
+                    }
+                    if (h == 0 && a.gather && !gather_cp) {
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) {
+                            const int t = int((it[f] >> 16) & 63u);
+                            const uint16_t *sp = W_SPERM + (it[f] & 0xffffu);
+#pragma unroll
+                            for (int k = 0; k < MAXT; ++k) x[f][k] = (k < t) ? buf[sp[k]] : 0.0;
+                        }
                         __syncthreads();  // the gather reads other lines' slots: nobody writes before everybody has read
                     } else if (h == 0) {
-                        const double *q = buf + (it & 0xffffu);
 #pragma unroll
-                        for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? q[k] : 0.0;
+                        for (int f = 0; f < NF; ++f) {
+                            const int t = int((it[f] >> 16) & 63u);
+                            const double *q = buf + (it[f] & 0xffffu);
+#pragma unroll
+                            for (int k = 0; k < MAXT; ++k) x[f][k] = (k < t) ? q[k] : 0.0;
+                        }
                     } else {
-                        const uint16_t *eo = W_SEO + (it & 0xffffu);
-                        const double *q = buf + (it >> 22);
 #pragma unroll
-                        for (int k = 0; k < MAXT; ++k) x[k] = (k < t) ? q[eo[k]] : 0.0;
+                        for (int f = 0; f < NF; ++f) {
+                            const int t = int((it[f] >> 16) & 63u);
+                            // the fibre's row offsets are 8-byte aligned in seo (host): four per shared-memory load
+                            const uint2 *eo4 = reinterpret_cast<const uint2 *>(W_SEO + (it[f] & 0xffffu));
+                            const double *q = buf + (it[f] >> 22);
+#pragma unroll
+                            for (int k4 = 0; k4 < MAXT; k4 += 4) {
+                                const uint2 e = eo4[k4 >> 2];
+                                x[f][k4] = (k4 < t) ? q[e.x & 0xffffu] : 0.0;
+                                x[f][k4 + 1] = (k4 + 1 < t) ? q[e.x >> 16] : 0.0;
+                                x[f][k4 + 2] = (k4 + 2 < t) ? q[e.y & 0xffffu] : 0.0;
+                                x[f][k4 + 3] = (k4 + 3 < t) ? q[e.y >> 16] : 0.0;
+                            }
+                        }
                     }
                 }
-                if (last && r0 + TG >= a.n_items[h]) {
-                    // every thread holds its fibre in registers: the buffer is free for the CTA's next function
+                if (last && r0 + TG * NF >= a.n_items[h]) {
+                    // every thread holds its fibres in registers: the buffer is free for the CTA's next function
                     fence_proxy_async();
                     __syncthreads();
                     if (!gather_cp && threadIdx.x == 0 && b + int(gridDim.x) < a.batch) issue_bulk(b + gridDim.x);
                 }
                 stamp(2 + 4 * h);
-                apply_fibre<MAXT, MODE, FMA, ROWS>(x, t, W_M(r0), __reduce_max_sync(0xffffffffu, t));
+                if constexpr (NF == 2 && !SEQ) {
+                    apply_fibre2<MAXT, FMA>(x[0], x[1], W_M(r0), __reduce_max_sync(0xffffffffu, tmax));
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) apply_fibre<MAXT, MODE, FMA, ROWS>(x[f], tf[f], W_M(r0 + f), __reduce_max_sync(0xffffffffu, tf[f]));
+                }
                 stamp(3 + 4 * h);
-                {   // the item is read again: nothing but the fibre stays in registers across the triangle code
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    // the item is read again: nothing but the fibres stays in registers across the triangle code
                     // (in particular not the "k < t" predicates, which the compiler would pack into a bit mask)
-                    const uint32_t it = *reinterpret_cast<const volatile uint32_t *>(W_SITEM + a.item_off[h] + r0 + threadIdx.x);
+                    const uint32_t it = *reinterpret_cast<const volatile uint32_t *>(W_SITEM + a.item_off[h] + r0 + f * TG + threadIdx.x);
                     const int t2 = int((it >> 16) & 63u);
                     if (last) {
-                        const uint16_t *eo = W_SEO + (it & 0xffffu);
-                        const int add = int(it >> 22);
+                        const uint2 *eo4 = reinterpret_cast<const uint2 *>(W_SEO + (it & 0xffffu));
+                        const unsigned add = it >> 22;
                         double *out = a.out + int64_t(b) * N;
                         if (a.scatter) {
+                            // blocks of eight rows: offsets (two loads), permutation look-ups (eight independent loads),
+                            // stores -- one dependent chain per block instead of one per element
 #pragma unroll
-                            for (int k = 0; k < MAXT; ++k)
-                                if (k < t2) out[W_SPERM[eo[k] + add]] = x[k];
+                            for (int k8 = 0; k8 < MAXT; k8 += 8) {
+                                const uint2 e0 = eo4[k8 >> 2], e1 = eo4[(k8 >> 2) + 1];
+                                const unsigned o[8] = {e0.x & 0xffffu, e0.x >> 16, e0.y & 0xffffu, e0.y >> 16,
+                                                       e1.x & 0xffffu, e1.x >> 16, e1.y & 0xffffu, e1.y >> 16};
+                                unsigned u[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) u[j] = (k8 + j < t2) ? W_SPERM[o[j] + add] : 0u;  // rows past the fibre hold padding
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (k8 + j < t2) out[u[j]] = x[f][k8 + j];
+                            }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < MAXT; ++k)
-                                if (k < t2) out[eo[k] + add] = x[k];
+                            for (int k4 = 0; k4 < MAXT; k4 += 4) {
+                                const uint2 e = eo4[k4 >> 2];
+                                if (k4 < t2) out[(e.x & 0xffffu) + add] = x[f][k4];
+                                if (k4 + 1 < t2) out[(e.x >> 16) + add] = x[f][k4 + 1];
+                                if (k4 + 2 < t2) out[(e.y & 0xffffu) + add] = x[f][k4 + 2];
+                                if (k4 + 3 < t2) out[(e.y >> 16) + add] = x[f][k4 + 3];
+                            }
                         }
                     } else {
                         double *buf = buf0 + ((oddN && !gather_cp) ? (b & 1) : 0);
@@ -227,20 +312,25 @@ __global__ void __launch_bounds__(TG, TG <= 384 ? 2 : 1) k_whole(const __grid_co
                             double *q = buf + (it & 0xffffu);
 #pragma unroll
                             for (int k = 0; k < MAXT; ++k)
-                                if (k < t2) q[k] = x[k];
+                                if (k < t2) q[k] = x[f][k];
                         } else {
-                            const uint16_t *eo = W_SEO + (it & 0xffffu);
+                            const uint2 *eo4 = reinterpret_cast<const uint2 *>(W_SEO + (it & 0xffffu));
                             double *q = buf + (it >> 22);
 #pragma unroll
-                            for (int k = 0; k < MAXT; ++k)
-                                if (k < t2) q[eo[k]] = x[k];
+                            for (int k4 = 0; k4 < MAXT; k4 += 4) {
+                                const uint2 e = eo4[k4 >> 2];
+                                if (k4 < t2) q[e.x & 0xffffu] = x[f][k4];
+                                if (k4 + 1 < t2) q[e.x >> 16] = x[f][k4 + 1];
+                                if (k4 + 2 < t2) q[e.y & 0xffffu] = x[f][k4 + 2];
+                                if (k4 + 3 < t2) q[e.y >> 16] = x[f][k4 + 3];
+                            }
                         }
                     }
                 }
                 stamp(4 + 4 * h);
                 // the permuting prefetch is issued by every thread once its own fibre is dead (issued in front of the
                 // triangle code it would push the 64-register fibre into local memory)
-                if (last && gather_cp && r0 + TG >= a.n_items[h] && b + int(gridDim.x) < a.batch) issue_gather(b + gridDim.x);
+                if (last && gather_cp && r0 + TG * NF >= a.n_items[h] && b + int(gridDim.x) < a.batch) issue_gather(b + gridDim.x);
             }
             if (!last) {
                 __syncthreads();

@@ -389,6 +389,12 @@ def test_c5_dx_eval_vs_oracle(T):
     {"use_whole": 1, "whole_threads": 768, "whole_rows": 4},
     {"use_whole": 1, "whole_threads": 384, "whole_order": 0, "whole_rows": 2},
     {"use_whole": 1, "whole_order": 63},
+    {"use_whole": 1, "whole_threads": 384, "whole_fibres": 2},
+    {"use_whole": 1, "whole_threads": 384, "whole_fibres": 2, "whole_order": 0},
+    {"use_whole": 1, "whole_threads_exact": 384, "whole_fibres_exact": 2, "whole_threads_fma": 768, "whole_fibres_fma": 1},
+    {"use_whole": 1, "whole_fibres": 3},
+    {"use_whole": 1, "whole_fibres": 3, "whole_order": 0},
+    {"use_whole": 1, "whole_threads": 768, "whole_fibres": 1},
     {"use_whole": 0, "use_slab": 2},
     {"use_whole": 0, "use_slab": 0},
     {"use_whole": 0, "use_cta_cap": 0},

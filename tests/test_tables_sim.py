@@ -77,15 +77,15 @@ def test_index_rejects_bad_sets(built_lib):
         nat.IndexTables(B, 2)
 
 
-@pytest.mark.parametrize("threads", [384, 768])
+@pytest.mark.parametrize("threads,fibres", [(384, 1), (768, 1), (384, 2), (384, 3)])
 @pytest.mark.parametrize("name", ["c1_d2n10", "d3n12_p1", "d3n6_inf", "d3n12_solve", "c2_d3n20_leja", "c4_d3n30", "d2n10_solve"])
-def test_emulated_whole_function_kernel_matches_reference(name, threads, built_lib):
-    """k_whole from its real item tables (rounds of 384 or 768 items in thread order) -- bit-exact."""
+def test_emulated_whole_function_kernel_matches_reference(name, threads, fibres, built_lib):
+    """k_whole from its real item tables (rounds of 384 or 768 items in thread order, one or two per thread) -- bit-exact."""
     g = load_case(name)
     m, n = int(g["m"]), int(g["n"])
     n1 = n + 1
     tabs = nat.IndexTables(g["A"].astype(np.int64), n)
-    tabs.whole_build(threads=threads)
+    tabs.whole_build(threads=threads, fibres=fibres)
     meta = tabs.whole_meta()
     assert meta["ok"] and meta["threads"] == threads
     if name == "c4_d3n30":
