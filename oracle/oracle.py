@@ -54,6 +54,7 @@ def lib():
         L.orc_sweep_upper_solve.argtypes = [_f64p, C.c_int, _f64p, _f64p, _i64p, C.c_int64, C.c_int, C.c_int, _i32p]
         L.orc_chebyshev2point.argtypes = [_f64p, _f64p, C.c_int64, _i64p, C.c_int64, C.c_int, C.c_int, _f64p]
         L.orc_newton2point.argtypes = [_f64p, _f64p, _f64p, C.c_int64, _i64p, C.c_int64, C.c_int, C.c_int, _f64p]
+        L.orc_roundtrip_batch.argtypes = [_f64p, _f64p, _f64p, _f64p, _f64p, _i64p, C.c_int64, C.c_int, _i32p, C.c_void_p, C.c_int64]
         _lib = L
     return _lib
 
@@ -229,6 +230,19 @@ class OracleTransform:
             out[self.P] = y
             return out
         return y
+
+    def roundtrip_batch(self, values):
+        """(coefficients, reconstruction) of a batch (B, N): fnt then ifnt, one OpenMP thread per function
+        (bench.py's "threads over functions" CPU figure; Newton basis, precomputation=True)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.ndim == 2 and v.shape[1] == self.N and self.precomputation and self.mats.get("Vx_ut") is None
+        prev = np.ascontiguousarray(np.concatenate([self.sw.neighbors(h)[0] for h in range(self.m)]))
+        coef = np.empty_like(v)
+        out = np.empty_like(v)
+        P = None if self.P is None else np.ascontiguousarray(self.P, dtype=np.int64)
+        lib().orc_roundtrip_batch(np.ascontiguousarray(self.mats["inv_Vx_lt"]), np.ascontiguousarray(self.mats["Vx_lt"]), v, coef, out,
+                                  self.sw.A, self.N, self.m, prev, None if P is None else P.ctypes.data, v.shape[0])
+        return coef, out
 
     # src/lpfun/transform.py:634-718, src/lpfun/core/molecules.py:222-309
     def dx(self, coeffs, i, k=1):
