@@ -148,6 +148,8 @@ int64_t lpfnt_plan_device_bytes(const lpfnt_plan *plan);
 int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
 /* options: "force_generic" (1 = route every op through the unbounded-n fallback kernels),
  *          "trace" (1 = record a CUDA-event pair around every kernel launch),
+ *          "dx_descending" (1 = lpfnt_dx folds every row from its last term down, the order of the reference on
+ *          p = inf sets with m > 1, src/lpfun/core/molecules.py:290-294; Transform sets it),
  *          "use_whole" (whole function in shared memory, one pass over HBM per transform, m = 2, 3:
  *          -1 = automatic (default: batches of >= 8 functions), 0 = off, 1 = always),
  *          "whole_threads" (-1 automatic: 384 threads and two CTAs per SM when two functions fit into shared memory,

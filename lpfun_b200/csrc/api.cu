@@ -82,6 +82,7 @@ struct lpfnt_plan {
     int64_t launches = 0;
     int64_t table_bytes = 0;
     int force_generic = 0;
+    int dx_descending = 0;                   // dx folds its rows from the last term down (the reference on p = inf sets with m > 1)
     // whole-function kernel (m = 2, 3): tables of HostIndex::whole on the device, one set for the exact forms
     // (index 0) and one for the fused-multiply-add forms (index 1): their best CTA shapes differ
     struct Whole {
@@ -217,11 +218,12 @@ struct SweepSpec {
     bool solve;
     bool fma;
     OperatorCache *op = nullptr;  // resolved once per call (run_any)
+    bool desc = false;            // upper mat-vec folded from the last term down (dx on p = inf sets, molecules.py:290-294)
 };
 
 int sweep_mode(const SweepSpec &s) {
     if (s.kind == LPFNT_LOWER) return s.solve ? kLowerSolve : kLowerMatvec;
-    return s.solve ? kUpperSolve : kUpperMatvec;
+    return s.solve ? kUpperSolve : (s.desc ? kUpperMatvecDesc : kUpperMatvec);
 }
 
 #define LAUNCH_CAP(cap, call8, call16, call24, call32) \
@@ -428,7 +430,7 @@ bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int>
     const bool want = p->use_whole == 1 || (p->use_whole == -1 && batch >= 8 && 3 * W.h.max_items >= 2 * W.h.threads);
     if (!want) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
-    if (spec.solve && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate
+    if ((spec.solve || spec.desc) && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate / descending fold
     if (W.h.fibres == 2 && !W.h.seq && sweep_mode(spec) != kLowerMatvec) return false;  // two fibres side by side: lower mat-vec only
     if (reinterpret_cast<uintptr_t>(in) & 15) return false;    // bulk copies need a 16-byte aligned batch
     return true;
@@ -497,7 +499,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     {
         size_t q = 0;
         const bool can_slab = p->use_slab && p->slabs.ok && !p->force_generic && p->m >= 2 &&
-                              pick_cap(std::max(p->slabs.max_t, 1)) > 0 && !(spec.solve && spec.kind == LPFNT_UPPER);
+                              pick_cap(std::max(p->slabs.max_t, 1)) > 0 && !((spec.solve || spec.desc) && spec.kind == LPFNT_UPPER);
         if (dims.size() >= 2 && dims[0] == 0 && dims[1] == 1 && can_slab) { passes.push_back({1, true}); q = 2; }
         for (; q < dims.size(); ++q) passes.push_back({dims[q], false});
     }
@@ -755,6 +757,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (!p || !name) { set_error("bad arguments"); return LPFNT_EINVAL; }
     if (std::strcmp(name, "force_generic") == 0) { p->force_generic = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "dx_descending") == 0) { p->dx_descending = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "host_chunk_bytes") == 0) { p->host_chunk_bytes = value <= 0 ? 0 : std::max<int64_t>(value, 1 << 16); return LPFNT_OK; }
     if (std::strcmp(name, "use_cta_cap") == 0) { p->use_cta_cap = value ? 1 : 0; return LPFNT_OK; }
@@ -950,6 +953,7 @@ int lpfnt_dx(lpfnt_plan *p, const double *in, double *out, int i, int k, int64_t
     int rc = check_ik(p, i, k);
     if (rc) return rc;
     SweepSpec spec{p->Dx_ut[k - 1].empty() ? nullptr : p->Dx_ut[k - 1].data(), LPFNT_UPPER, false, false};
+    spec.desc = p->dx_descending != 0;
     return run_any(p, spec, std::vector<int>{i}, in, out, batch, false, false, on_device, stream);
 }
 

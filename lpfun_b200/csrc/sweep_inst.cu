@@ -114,6 +114,7 @@ cudaError_t launch_group_sweep<T>(int mode, bool fma, const GroupSweepArgs &a, c
         case kLowerSolve: return group_launch<kLowerSolve, false>(a, M, batch, s);
         case kUpperSolve: return group_launch<kUpperSolve, false>(a, M, batch, s);
         case kUpperSolveDesc: return group_launch<kUpperSolveDesc, false>(a, M, batch, s);
+        case kUpperMatvecDesc: return group_launch<kUpperMatvecDesc, false>(a, M, batch, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -127,6 +128,7 @@ cudaError_t launch_line_sweep<T>(int mode, bool fma, const LineSweepArgs &a, con
         case kUpperMatvec: return fma ? line_launch<kUpperMatvec, true>(a, M, batch, s) : line_launch<kUpperMatvec, false>(a, M, batch, s);
         case kLowerSolve: return line_launch<kLowerSolve, false>(a, M, batch, s);
         case kUpperSolve: return line_launch<kUpperSolve, false>(a, M, batch, s);
+        case kUpperMatvecDesc: return line_launch<kUpperMatvecDesc, false>(a, M, batch, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -24,8 +24,10 @@ enum SweepMode : int {
     kLowerSolve = 2,   // out_k = (x_k - sum_{j<k} L[k,j] out_j)/L[k,k] (fnt, precomputation=False)
     kUpperSolve = 3,   // out_k = (x_k - (U[k,k]*0 + sum_{j>k} U[k,j] out_j))/U[k,k], j ascending (coordinate 0:
                        // transform_ut_1d / the 1d stage of transform_ut_2d/3d/md, atoms.py:54-69, 372-385)
-    kUpperSolveDesc = 4  // same, j DEscending: coordinates >= 1 accumulate the leaders last-to-first
+    kUpperSolveDesc = 4, // same, j DEscending: coordinates >= 1 accumulate the leaders last-to-first
                          // (atoms.py:391-402, 975-1003)
+    kUpperMatvecDesc = 5 // out_k = sum_{j>=k} U[k,j] x_j folded from the LAST j down to k: dx on p = inf sets with m > 1, where the
+                         // reference runs dtransform_max on reversed arrays (src/lpfun/core/molecules.py:290-294)
 };
 
 // Packed triangle with COMPILE-TIME offsets, independent of n:
@@ -103,6 +105,18 @@ __device__ __forceinline__ void apply_fibre(double (&x)[MAXT], const int t, cons
 #pragma unroll
                 for (int k = 0; k < j; ++k) x[k] = mac<FMA>(x[k], M.v[j * (j + 1) / 2 + k], xj);
                 x[j] = mac<FMA>(0.0, M.v[j * (j + 1) / 2 + j], xj);
+            }
+        }
+    } else if constexpr (MODE == kUpperMatvecDesc) {
+        // row form, rows ascending (out_k only reads x_j, j >= k, so it may overwrite x_k), every row folded from j = t - 1 down
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) {
+            if (k < t) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = MAXT - 1; j >= k; --j)
+                    if (j < t) s = mac<FMA>(s, M.v[j * (j + 1) / 2 + k], x[j]);
+                x[k] = s;
             }
         }
     } else if constexpr (MODE == kLowerSolve) {
@@ -505,6 +519,13 @@ __global__ void __launch_bounds__(128) k_sweep_generic(const GenericArgs a) {
             const double *row = a.mat + int64_t(k) * n1 - int64_t(k) * (k - 1) / 2;
             double acc = 0.0;
             for (int q = k; q < t; ++q) acc = mac_rt(acc, row[q - k], rd(q), a.fma);
+            wr(k, acc);
+        }
+    } else if (a.mode == kUpperMatvecDesc) {
+        for (int k = 0; k < t; ++k) {
+            const double *row = a.mat + int64_t(k) * n1 - int64_t(k) * (k - 1) / 2;
+            double acc = 0.0;
+            for (int q = t - 1; q >= k; --q) acc = mac_rt(acc, row[q - k], rd(q), a.fma);
             wr(k, acc);
         }
     } else if (a.mode == kLowerSolve) {

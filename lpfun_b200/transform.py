@@ -153,6 +153,10 @@ class Transform:
         nat.check(rc)
         if self._Vx_ut is not None:
             nat.check(L.lpfnt_plan_set_upper_factors(plan, self._Vx_ut.ctypes.data, nat.ptr(self._inv_Vx_ut), int(self._basis == "chebyshev")))
+        if np.isinf(self._p) and self._m > 1:
+            # the reference differentiates p = inf sets on reversed arrays (molecules.py:290-294): every row of dx is
+            # folded from its last term down; reproduced so that dx is bit-identical there too
+            nat.check(L.lpfnt_plan_set_option(plan, b"dx_descending", 1))
         return plan
 
     def close(self):

@@ -66,15 +66,12 @@ def test_golden_case(T, name):
     tf = make(T, g)  # default: FMA ifnt
     assert relmax(tf.ifnt(g["fnt"]), g["ifnt"]) <= TOL_IFNT_FMA
     # --- dx / dxT ---
-    inf_multi = np.isinf(float(g["p"])) and m > 1  # reference folds descending there (molecules.py:290-294)
+    # p = inf, m > 1: the reference folds every row of dx from its last term down (molecules.py:290-294); so does the plan
     for key in g.files:
         if key.startswith("dx_"):
             _, i, k = key.split("_")
             out = t.dx(g["fnt"][0], int(i), int(k))
-            if inf_multi:
-                assert relmax(out, g[key]) <= 1e-13, key
-            else:
-                assert np.array_equal(out, g[key]), key
+            assert np.array_equal(out, g[key]), key
         elif key.startswith("dxT_"):
             _, i, k = key.split("_")
             assert np.array_equal(t.dxT(g["rnd"], int(i), int(k)), g[key]), key
@@ -108,15 +105,11 @@ def test_golden_case_chebyshev(T, name, generic):
     tf = make(T, g)
     tf.set_option("force_generic", generic)
     assert relmax(tf.ifnt(g["fnt"]), g["ifnt"]) <= TOL_IFNT_FMA
-    inf_multi = np.isinf(float(g["p"])) and m > 1
     for key in g.files:
         if key.startswith("dx_"):
             _, i, k = key.split("_")
             out = t.dx(g["fnt"][0], int(i), int(k))
-            if inf_multi:
-                assert relmax(out, g[key]) <= 1e-13, key
-            else:
-                assert np.array_equal(out, g[key]), key
+            assert np.array_equal(out, g[key]), key
         elif key.startswith("dxT_"):
             _, i, k = key.split("_")
             assert np.array_equal(t.dxT(g["rnd"], int(i), int(k)), g[key]), key
@@ -179,8 +172,7 @@ def test_generic_kernels_match_too(T, name):
     assert np.array_equal(t.fnt(g["values"]), g["fnt"])
     assert np.array_equal(t.ifnt(g["fnt"]), g["ifnt"])
     m = int(g["m"])
-    if not (np.isinf(float(g["p"])) and m > 1):
-        assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
+    assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
     assert np.array_equal(t.dxT(g["rnd"], 0, 1), g["dxT_0_1"])
     assert relmax(t.eval(g["fnt"][0], g["points"]), g["eval"]) <= TOL_EVAL
     t.close()
@@ -263,18 +255,19 @@ def test_error_behaviour(T):
 
 
 # ---------------------------------------------------------------------------------------
-# the reference's own property tests (test.py:45-151), Newton basis, both precomputation modes
+# the reference's own property tests (test.py:45-151) over its own parameter grid (test.py:8-13): both bases, both
+# precomputation modes
 # ---------------------------------------------------------------------------------------
-GRID = [(m, p, pr) for m in (1, 2, 3, 4, 5, 6) for p in (1.0, 2.0, np.inf) for pr in (True, False)]
+GRID = [(m, p, basis, pr) for m in (1, 2, 3, 4, 5, 6) for p in (1.0, 2.0, np.inf) for basis in ("newton", "chebyshev") for pr in (True, False)]
 
 
-@pytest.mark.parametrize("m, p, pr", GRID)
-def test_reference_property_suite(T, m, p, pr):
+@pytest.mark.parametrize("m, p, basis, pr", GRID)
+def test_reference_property_suite(T, m, p, basis, pr):
     rng = np.random.default_rng(100 * m + int(pr))
     for n in (4, 6, 8) if m < 6 else (4, 5):
         if np.isinf(p) and (n + 1) ** m > 300000:
             continue
-        t = T(m, n, p, precomputation=pr, precompilation=False, colex_order=False, report=False)
+        t = T(m, n, p, basis=basis, precomputation=pr, precompilation=False, colex_order=False, report=False)
         N = len(t)
         # test_fnt_ifnt
         f = rng.random(N)
@@ -294,7 +287,7 @@ def test_reference_property_suite(T, m, p, pr):
                 assert abs(np.dot(t.dx(x, i, k), y) - np.dot(x, t.dxT(y, i, k))) < 1e-6
         t.close()
         # test_eval (degree n+1, cubic)
-        t = T(m, n + 1, p, precomputation=pr, precompilation=False, colex_order=False, report=False)
+        t = T(m, n + 1, p, basis=basis, precomputation=pr, precompilation=False, colex_order=False, report=False)
         c = t.fnt(np.sum(t.grid ** 3, axis=1))
         pts = rng.random((10, m))
         assert np.max(np.abs(t.eval(c, pts) - np.sum(pts ** 3, axis=1))) < 1e-6
@@ -412,8 +405,7 @@ def test_alternative_kernel_families(T, name, opts):
     assert np.array_equal(t.ifnt(g["fnt"]), g["ifnt"])
     assert np.array_equal(t.fnt(np.tile(g["rnd"], (5, 1)))[3], g["fnt_rnd"])
     m = int(g["m"])
-    if not (np.isinf(float(g["p"])) and m > 1):
-        assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
+    assert np.array_equal(t.dx(g["fnt"][0], m - 1, 1), g[f"dx_{m-1}_1"])
     assert np.array_equal(t.dxT(g["rnd"], m - 1, 1), g[f"dxT_{m-1}_1"])
     t.close()
 
@@ -489,13 +481,41 @@ def test_size_boundaries_vs_oracle(T, m, n, p):
     c = t.fnt(v)
     assert np.array_equal(c, np.stack([o.fnt(r) for r in v]))
     assert np.array_equal(t.ifnt(c), np.stack([o.ifnt(r) for r in c]))
-    if n >= 1 and not (np.isinf(p) and m > 1):
-        assert np.array_equal(t.dx(c[0], m - 1, 1), o.dx(c[0], m - 1, 1))
+    if n >= 1:
+        assert np.array_equal(t.dx(c[0], m - 1, 1), o.dx(c[0], m - 1, 1))  # p = inf: folded descending, like the reference
         assert np.array_equal(t.dxT(v[0], 0, 1), o.dxT(v[0], 0, 1))
     pts = rng.uniform(-1, 1, (33, m))
-    # eval at n >= 30 mixes terms of very different size: compare to the reference-order sum with a looser bound
-    assert relmax(t.eval(c[0], pts), o.eval(c[0], pts)) <= (1e-12 if n < 25 else 1e-9)
+    # eval on random (non-smooth) coefficients at n >= 25 mixes terms of very different size, and the reference's own flat
+    # left-to-right sum loses digits there: judge both against an extended-precision truth (x87 80-bit long double, every
+    # product and sum in long double) -- the GPU's nested Horner form must be at least as accurate as the reference order
+    truth = eval_truth_longdouble(c[0], o.x, pts, o.A)
+    scale = float(np.max(np.abs(truth)))
+    got, ref = t.eval(c[0], pts), o.eval(c[0], pts)
+    err_gpu = float(np.max(np.abs(got.astype(np.longdouble) - truth)))
+    err_ref = float(np.max(np.abs(ref.astype(np.longdouble) - truth)))
+    assert err_gpu <= max(err_ref, 1e-12 * scale), (err_gpu / scale, err_ref / scale)
+    if n < 25:
+        assert relmax(got, ref) <= 1e-12
     t.close()
+
+
+def eval_truth_longdouble(c, nodes, pts, A):
+    """newton2point (src/lpfun/utils.py:132-162) in np.longdouble: basis tables by the same recurrence, flat sum."""
+    ld = np.longdouble
+    P, m = pts.shape
+    n1 = len(nodes)
+    basis = np.ones((P, m, n1), dtype=ld)
+    for q in range(1, n1):
+        basis[:, :, q] = basis[:, :, q - 1] * (pts.astype(ld) - ld(nodes[q - 1]))
+    out = np.zeros(P, dtype=ld)
+    cl = c.astype(ld)
+    for b0 in range(0, len(A), 4096):
+        blk = A[b0:b0 + 4096]
+        prod = np.ones((P, len(blk)), dtype=ld)
+        for j in range(m):
+            prod *= basis[:, j, :][:, blk[:, j]]
+        out += prod @ cl[b0:b0 + 4096]
+    return out
 
 
 def test_batch_beyond_the_grid_limit(T):
