@@ -64,6 +64,12 @@ struct lpfnt_plan {
     double *d_cpad = nullptr;       // padded coefficient layout of the eval kernel
     int32_t num_eval_blocks = 0;
     int use_eval_block = 1;
+    int use_eval_split = -1;        // few points: split the index trie over CTAs (-1 automatic, 0 off, 1 always)
+    std::vector<uint8_t> h_line_alpha;   // host copy (the split levels are derived on first use)
+    struct EvalSplit { int L = 0; int32_t num_sub = 0; int32_t *d_l0 = nullptr; uint8_t *d_alpha = nullptr; };
+    std::vector<EvalSplit> eval_splits;  // one per level L already built
+    std::vector<int64_t> eval_split_counts;  // subtrees per level L = 1 .. m-1 (filled on first use)
+    int64_t eval_padded = 0;        // doubles of the padded coefficient layout (d_cpad is allocated by the first eval that needs it)
     int64_t *d_A = nullptr;       // only for the generic eval fallback (uploaded lazily)
     double *d_nodes = nullptr;
     DeviceDim dd[kMaxDim + 1];
@@ -585,6 +591,44 @@ int run_any(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, 
     return run_any(p, std::vector<SweepSpec>{spec}, dims, in, out, batch, gather, scatter, on_device, stream);
 }
 
+
+// Subtrees of the index trie below its top L levels (see k_eval_sub): runs of lines with equal (a_{m-L}, .., a_{m-1}).
+int eval_split_level(lpfnt_plan *p, int L, const lpfnt_plan::EvalSplit **out) {
+    for (const auto &es : p->eval_splits)
+        if (es.L == L) { *out = &es; return LPFNT_OK; }
+    const int m = p->m, w = m - 1;
+    std::vector<int32_t> l0;
+    std::vector<uint8_t> al;
+    const uint8_t *A = p->h_line_alpha.data();
+    for (int64_t l = 0; l < p->N1; ++l) {
+        const uint8_t *k = A + l * w + (w - L);
+        if (l == 0 || std::memcmp(k, A + (l - 1) * w + (w - L), size_t(L)) != 0) {
+            l0.push_back(int32_t(l));
+            al.insert(al.end(), k, k + L);
+        }
+    }
+    l0.push_back(int32_t(p->N1));
+    lpfnt_plan::EvalSplit es;
+    es.L = L;
+    es.num_sub = int32_t(l0.size() - 1);
+    int rc;
+    if ((rc = upload(&es.d_l0, l0.data(), l0.size(), p))) return rc;
+    if ((rc = upload(&es.d_alpha, al.data(), al.size(), p))) return rc;
+    p->eval_splits.push_back(es);
+    *out = &p->eval_splits.back();
+    return LPFNT_OK;
+}
+
+// number of subtrees at level L without building the tables
+int64_t eval_split_count(const lpfnt_plan *p, int L) {
+    const int w = p->m - 1;
+    const uint8_t *A = p->h_line_alpha.data();
+    int64_t g = 0;
+    for (int64_t l = 0; l < p->N1; ++l)
+        if (l == 0 || std::memcmp(A + l * w + (w - L), A + (l - 1) * w + (w - L), size_t(L)) != 0) ++g;
+    return g;
+}
+
 std::vector<int> all_dims(int m) {
     std::vector<int> d(m);
     for (int i = 0; i < m; ++i) d[i] = i;
@@ -697,14 +741,14 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if ((rc = upload(&p->d_eval_line, reinterpret_cast<const int2 *>(hx.eval_line.data()), hx.eval_line.size(), p))) return fail(rc);
         if ((rc = upload(&p->d_eval_block, reinterpret_cast<const int4 *>(hx.eval_block.data()), hx.eval_block.size(), p))) return fail(rc);
         p->num_eval_blocks = int32_t(hx.eval_block.size());
-        if (cudaMalloc(reinterpret_cast<void **>(&p->d_cpad), sizeof(double) * size_t(hx.eval_padded + 4)) != cudaSuccess) { set_error("cudaMalloc(cpad) failed"); return fail(LPFNT_ENOMEM); }
-        p->table_bytes += int64_t(sizeof(double)) * (hx.eval_padded + 4);
+        p->eval_padded = hx.eval_padded;
     }
     if (!hx.line_alpha.empty()) {
         // the eval kernel stages the alpha bytes in 4-byte words: pad the table so that its last word is complete
         std::vector<uint8_t> al(hx.line_alpha);
         al.resize(((al.size() + 3) & ~size_t(3)) + 4, 0);
         if ((rc = upload(&p->d_line_alpha, al.data(), al.size(), p))) return fail(rc);
+        p->h_line_alpha = hx.line_alpha;
     }
     // the generic eval needs A on the device: keep a host copy when the fast path cannot run, or when the set is small
     // enough for the copy not to matter (force_generic in the tests)
@@ -723,6 +767,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
+    for (auto &es : p->eval_splits) { cudaFree(es.d_l0); cudaFree(es.d_alpha); }
     free_whole(p, 0);
     free_whole(p, 1);
     cudaFree(p->d_perm16);
@@ -759,6 +804,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     if (std::strcmp(name, "trace") == 0) { p->trace = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "dx_descending") == 0) { p->dx_descending = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "eval_block") == 0) { p->use_eval_block = value ? 1 : 0; return LPFNT_OK; }
+    if (std::strcmp(name, "eval_split") == 0) { p->use_eval_split = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
     if (std::strcmp(name, "host_chunk_bytes") == 0) { p->host_chunk_bytes = value <= 0 ? 0 : std::max<int64_t>(value, 1 << 16); return LPFNT_OK; }
     if (std::strcmp(name, "use_cta_cap") == 0) { p->use_cta_cap = value ? 1 : 0; return LPFNT_OK; }
     if (std::strcmp(name, "timeline") == 0) {
@@ -975,7 +1021,7 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
     double *dv = values;
     // the Chebyshev basis only has the block-staged fast kernel (and the generic fallback)
     const bool fast = !p->force_generic && (p->n + 1 <= kMaxRegT) && p->m <= kEvalMaxM && p->n <= 255 && (p->m == 1 || p->d_line_alpha) &&
-                      (!p->chebyshev_eval || (p->use_eval_block && p->d_eval_block && p->d_cpad));
+                      (!p->chebyshev_eval || (p->use_eval_block && p->d_eval_block && p->eval_padded > 0));
     const size_t cb = size_t(p->N) * sizeof(double), pb = size_t(P) * p->m * sizeof(double), vb = size_t(P) * sizeof(double);
     if (!on_device) {
         int rc = ensure_ws(p, 0, cb + pb);
@@ -987,8 +1033,52 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
         CK(cudaMemcpyAsync(w + p->N, points, pb, cudaMemcpyHostToDevice, s));
         dc = w; dp = w + p->N; dv = p->ws[1];
     }
-    if (fast) {
-        const bool blocked = p->use_eval_block && p->d_eval_block && p->d_cpad && (p->m == 1 || p->d_line_alpha);
+    // few points: one thread per point cannot fill the GPU (the kernels below walk all N coefficients per thread) -- cut the
+    // index trie into at least ~4 subtrees per SM and point tile, evaluate them side by side, combine in basis form
+    bool split_done = false;
+    if (fast && !p->chebyshev_eval && p->m >= 2 && p->use_eval_split != 0 && !p->h_line_alpha.empty()) {
+        const int64_t tiles = (P + 255) / 256;
+        // enough subtrees to fill the GPU, and subtrees short enough (<= ~512 coefficients) for the per-thread chains
+        const int64_t want = std::max<int64_t>((int64_t(4) * p->num_sms + tiles - 1) / tiles, p->N / 512);
+        if (p->use_eval_split == 1 || (tiles < 2 * p->num_sms && P <= 8192)) {
+            int L = 0;
+            int64_t G = 0;
+            if (p->eval_split_counts.empty())
+                for (int l = 1; l <= p->m - 1; ++l) p->eval_split_counts.push_back(eval_split_count(p, l));
+            for (int l = 1; l <= p->m - 1; ++l) {
+                const int64_t g = p->eval_split_counts[l - 1];
+                if (g > 65536 && L > 0) break;
+                L = l; G = g;
+                if (g >= want) break;
+            }
+            if (L > 0 && G > 1) {
+                const lpfnt_plan::EvalSplit *es = nullptr;
+                int rc = eval_split_level(p, L, &es);
+                if (rc) return rc;
+                // partial sums: G doubles per point, at most 256 MB at a time
+                const int64_t pc = std::max<int64_t>(1, std::min<int64_t>(P, (int64_t(256) << 20) / (8 * G)));
+                rc = ensure_ws(p, 2, size_t(G) * size_t(pc) * sizeof(double));
+                if (rc) return rc;
+                for (int64_t q0 = 0; q0 < P; q0 += pc) {
+                    const int64_t np = std::min(pc, P - q0);
+                    EvalSubArgs a{dc, dp + q0 * p->m, p->ws[2], p->d_line_off, p->d_line_alpha, es->d_l0, es->d_alpha, dv + q0, np, es->num_sub, L, p->m, p->n + 1};
+                    trace_begin(p, 1300, s);
+                    cudaError_t e = launch_eval_split(a, p->nodes.data(), p->n + 1, s);
+                    trace_end(p, s);
+                    p->launches += 2;
+                    if (e != cudaSuccess) { set_error(std::string("eval split launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+                }
+                split_done = true;
+            }
+        }
+    }
+    if (split_done) {
+    } else if (fast) {
+        const bool blocked = p->use_eval_block && p->d_eval_block && p->eval_padded > 0 && (p->m == 1 || p->d_line_alpha);
+        if (blocked && !p->d_cpad) {
+            if (cudaMalloc(reinterpret_cast<void **>(&p->d_cpad), sizeof(double) * size_t(p->eval_padded + 4)) != cudaSuccess) { set_error("cudaMalloc(cpad) failed"); return LPFNT_ENOMEM; }
+            p->table_bytes += int64_t(sizeof(double)) * (p->eval_padded + 4);
+        }
         if (blocked) {
             EvalPadArgs pa{dc, p->d_cpad, p->d_line_off, p->d_eval_line, int32_t(p->N1)};
             trace_begin(p, 1100, s);

@@ -60,6 +60,28 @@ cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n
     return cudaErrorInvalidValue;
 }
 
+namespace {
+template <int MAXT>
+cudaError_t eval_split_launch(const EvalSubArgs &a, const double *nodes, int n1, cudaStream_t s) {
+    NodeTable<MAXT> nt;
+    for (int k = 0; k < MAXT; ++k) nt.v[k] = (k < n1) ? nodes[k] : 0.0;
+    const int64_t pairs = int64_t(a.num_sub) * a.num_points;
+    k_eval_sub<MAXT><<<unsigned((pairs + 127) / 128), 128, 0, s>>>(a, nt);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_eval_combine<MAXT><<<unsigned(a.num_points), 256, 0, s>>>(a, nt);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_eval_split(const EvalSubArgs &a, const double *nodes, int n1, cudaStream_t s) {
+    if (n1 <= 8) return eval_split_launch<8>(a, nodes, n1, s);
+    if (n1 <= 16) return eval_split_launch<16>(a, nodes, n1, s);
+    if (n1 <= 24) return eval_split_launch<24>(a, nodes, n1, s);
+    if (n1 <= 32) return eval_split_launch<32>(a, nodes, n1, s);
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_eval_pad(const EvalPadArgs &a, cudaStream_t s) {
     k_eval_pad<<<(a.num_lines + 3) / 4, 128, 0, s>>>(a);
     return cudaGetLastError();

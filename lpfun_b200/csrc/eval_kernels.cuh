@@ -346,6 +346,96 @@ __global__ void __launch_bounds__(THREADS, MAXT > 24 ? 4 : 1) k_eval_block(const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Few points (P << 256 * #SM): the kernels above give every point ONE thread that walks all N coefficients -- eval of the
+// README's "10 random points" at d = 6, n = 20 ran 240 ms on one CTA.  Split path: the index trie is cut below its top L
+// levels into G subtrees (fixed (a_{m-L}, .., a_{m-1}); contiguous runs of lines, since the lines are in colex order);
+//   k_eval_sub     : thread <-> (subtree, point): nested Horner over the subtree's lines -> partial[g][p]
+//   k_eval_combine : thread <-> point: value = sum_g partial[g][p] * prod_{j >= m-L} N_{a_j(g)}(x_j)   (basis form, in g order)
+// Deterministic (no atomics).  Newton basis.
+// ---------------------------------------------------------------------------------------
+struct EvalSubArgs {
+    const double *coeffs;       // N
+    const double *points;       // P x m
+    double *partial;            // G x P
+    const int32_t *line_off;    // N_1 + 1
+    const uint8_t *line_alpha;  // N_1 x (m-1)
+    const int32_t *sub_l0;      // G + 1: first line of every subtree
+    const uint8_t *sub_alpha;   // G x L: (a_{m-L}, .., a_{m-1}) of every subtree
+    double *values;             // P
+    int64_t num_points;
+    int32_t num_sub, L, m, n1;
+};
+
+#ifdef LPFNT_EVAL_TU
+template <int MAXT>
+__global__ void __launch_bounds__(128) k_eval_sub(const EvalSubArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
+    const int64_t idx = int64_t(blockIdx.x) * 128 + threadIdx.x;
+    if (idx >= int64_t(a.num_sub) * a.num_points) return;
+    const int g = int(idx / a.num_points);
+    const int64_t p = idx - int64_t(g) * a.num_points;
+    const int m = a.m, lev = m - a.L;  // levels 0 .. lev-1 are folded here
+    double x[kEvalMaxM], acc[kEvalMaxM];
+    for (int j = 0; j < lev; ++j) { x[j] = a.points[p * m + j]; acc[j] = 0.0; }
+    double d0[MAXT];
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) d0[k] = x[0] - nodes.v[k];
+    for (int l = a.sub_l0[g + 1] - 1; l >= a.sub_l0[g]; --l) {
+        const int off = a.line_off[l], t = a.line_off[l + 1] - off;
+        // all coefficients of the line are requested before the Horner chain needs the first one
+        double cv[MAXT];
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) cv[k] = (k < t) ? __ldg(a.coeffs + off + k) : 0.0;
+        double s = 0.0;
+#pragma unroll
+        for (int k = MAXT - 1; k >= 0; --k)
+            if (k < t) s = __fma_rn(s, d0[k], cv[k]);
+        const uint8_t *al = a.line_alpha + int64_t(l) * (m - 1);
+        bool carry = true;
+        for (int j = 1; j < lev && carry; ++j) {
+            const int aj = al[j - 1];
+            const double below = (j == 1) ? s : acc[j - 1];
+            acc[j] = __fma_rn(acc[j], x[j] - nodes.v[aj], below);
+            if (j > 1) acc[j - 1] = 0.0;
+            carry = (aj == 0);
+        }
+        if (lev == 1) acc[0] = s;  // one line per subtree
+    }
+    a.partial[idx] = acc[lev - 1];
+}
+
+// one CTA of 256 threads per point: thread i sums the subtrees i, i + 256, ... in order, then a fixed-shape tree over the
+// 256 partial sums (deterministic)
+template <int MAXT>
+__global__ void __launch_bounds__(256) k_eval_combine(const EvalSubArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
+    __shared__ double B[kEvalMaxM][MAXT];  // Newton basis values N_k(x_j) of the top L coordinates (utils.py:148-151)
+    __shared__ double red[256];
+    const int64_t p = blockIdx.x;
+    const int m = a.m, L = a.L;
+    if (threadIdx.x < L) {
+        const int j = threadIdx.x;
+        const double xj = a.points[p * m + (m - L + j)];
+        B[j][0] = 1.0;
+        for (int k = 1; k < a.n1; ++k) B[j][k] = B[j][k - 1] * (xj - nodes.v[k - 1]);
+    }
+    __syncthreads();
+    double v = 0.0;
+    for (int g = threadIdx.x; g < a.num_sub; g += 256) {
+        double w = a.partial[int64_t(g) * a.num_points + p];
+        for (int j = 0; j < L; ++j) w *= B[j][a.sub_alpha[g * L + j]];
+        v += w;
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.values[p] = red[0];
+}
+#endif
+
 // Fallback without unrolling limits (any n, any m): flat sum in the reference's own order,
 // thread per point, basis table in local memory.  A: int64 (N x m) multi-indices on the device.
 struct EvalGenericArgs {

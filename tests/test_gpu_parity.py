@@ -371,7 +371,37 @@ def test_c5_dx_eval_vs_oracle(T):
         d = t.dx(c, i, 1)
         assert np.array_equal(d, g[f"dx_{i}_1"])
     want = o.eval(g["dx_0_1"], g["x"], pts, 20)
-    assert relmax(t.eval(g["dx_0_1"], pts), want) <= TOL_EVAL
+    for split in (0, 1, -1):  # block-staged kernel / split path (subtrees over CTAs + basis-form combination) / automatic
+        t.set_option("eval_split", split)
+        assert relmax(t.eval(g["dx_0_1"], pts), want) <= TOL_EVAL, split
+    t.close()
+
+
+@pytest.mark.parametrize("m,n,p", [(2, 10, 2.0), (3, 12, 1.0), (3, 30, 2.0), (4, 9, np.inf), (5, 6, 2.0), (6, 8, 2.0), (2, 31, 2.0)])
+@pytest.mark.parametrize("P", [1, 10, 300])
+def test_eval_few_points_split_path(T, m, n, p, P):
+    """Few points: the index trie is cut into subtrees that are evaluated side by side and combined in basis form
+    (k_eval_sub + k_eval_combine) -- against the oracle's reference-order sum and against the one-thread-per-point kernels."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(31 * m + n + P)
+    t = T(m, n, lp_degree=p, report=False)
+    o = O.OracleTransform(m, n, p)
+    c = rng.standard_normal(len(t)) / (1.0 + np.arange(len(t))) ** 0.5
+    pts = rng.uniform(-1, 1, (P, m))
+    want = o.eval(c, pts)
+    t.set_option("eval_split", 1)
+    l0 = t.launch_count
+    got = t.eval(c, pts)
+    assert (t.launch_count - l0) % 2 == 0 and t.launch_count > l0  # the split path really ran (two launches per chunk of points)
+    tol = 1e-12 if n < 25 else 1e-10
+    assert relmax(got, want) <= tol
+    import torch
+
+    dev = t.eval(torch.as_tensor(c, device="cuda"), torch.as_tensor(pts, device="cuda"))  # device tensors: same kernels
+    assert np.array_equal(dev.cpu().numpy(), got)
+    t.set_option("eval_split", 0)
+    assert relmax(t.eval(c, pts), got) <= tol
     t.close()
 
 
