@@ -152,9 +152,10 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          p = inf sets with m > 1, src/lpfun/core/molecules.py:290-294; Transform sets it),
  *          "use_whole" (whole function in shared memory, one pass over HBM per transform, m = 2, 3:
  *          -1 = automatic (default: batches of >= 8 functions), 0 = off, 1 = always),
- *          "whole_threads" (-1 automatic: 384 threads and two CTAs per SM when two functions fit into shared memory,
- *          else 768 and one; or 384 / 768), "whole_order" (item order, see lpfnt_index_whole_build),
- *          "whole_rows" (rows of the triangle code folded side by side: 2 or 4; -1 automatic),
+ *          "whole_threads" / "whole_fibres" / "whole_order" (CTA shape of the whole-function kernel: 384 or 768 threads;
+ *          1 item per thread, 2 = two of equal length class folded side by side, 3 = a long and a short one folded one
+ *          after the other; item order, see lpfnt_index_whole_build; -1 = automatic; the suffixes "_exact" / "_fma"
+ *          address the tables of the exact / the fused-multiply-add forms only),
  *          "use_slab" (coordinates 0 and 1 in one pass over slabs of planes, any m >= 2: 1 = when the slabs
  *          fill the CTA (default), 0 = off, 2 = always), "use_cta_cap" (k_sweep_groups: per-CTA row capacity),
  *          "eval_block" (0 = non-staged eval kernel), "timeline" (development: clock64 stamps of the

@@ -437,7 +437,7 @@ bool whole_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int>
     if (!want) return false;
     for (int q = 0; q < p->m; ++q) if (dims[q] != q) return false;
     if ((spec.solve || spec.desc) && spec.kind == LPFNT_UPPER) return false;  // fold order changes with the coordinate / descending fold
-    if (W.h.fibres == 2 && !W.h.seq && sweep_mode(spec) != kLowerMatvec) return false;  // two fibres side by side: lower mat-vec only
+    if (W.h.fibres == 2 && sweep_mode(spec) != kLowerMatvec) return false;  // two fibres per thread: lower mat-vec only
     if (reinterpret_cast<uintptr_t>(in) & 15) return false;    // bulk copies need a 16-byte aligned batch
     return true;
 }
@@ -456,11 +456,9 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     a.n_elem = int32_t(p->N); a.m = p->m;
     a.dbg = p->d_timeline;
     const bool timeline = p->d_timeline != nullptr;
-    // rows folded side by side (one fibre per thread): 4 for the fused form (its chains are latency bound), 2 for the
-    // exact form (twice the instructions per term already)
-    const int rows = W.h.fibres == 2 ? 2 : (p->wcfg[which].rows > 0 ? p->wcfg[which].rows : (spec.fma ? 4 : 2));
+    const int rows = 2;  // rows folded side by side
     const int modekind = mode == kLowerMatvec ? (spec.fma ? 1 : 0) : mode == kUpperMatvec ? (spec.fma ? 3 : 2) : 4;
-    const int shape = (W.h.threads == 384 ? 0 : 1) + (W.h.fibres == 2 ? (W.h.seq ? 6 : 2) : (rows == 4 ? 4 : 0));  // < 8
+    const int shape = (W.h.threads == 384 ? 0 : 1) + (W.h.fibres == 2 ? (W.h.seq ? 6 : 2) : 0);  // < 8
     const int key = ((cap / 8 - 1) * 5 + modekind) * 8 + shape + (timeline ? 160 : 0);                               // < 320
     const int fibres_code = W.h.fibres == 2 ? (W.h.seq ? 3 : 2) : 1;
     const bool set_attr = !p->whole_attr_set[key];

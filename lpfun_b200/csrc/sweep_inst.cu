@@ -67,17 +67,12 @@ cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibre
     }
     if (fibres == 3) {
         if (threads != 384) return cudaErrorInvalidValue;
-        switch (mode) {
-            case kLowerMatvec: return fma ? whole_launch_two<kLowerMatvec, true, true>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, true>(timeline, a, M, grid, smem, set_attr, s);
-            case kUpperMatvec: return fma ? whole_launch_two<kUpperMatvec, true, true>(false, a, M, grid, smem, set_attr, s) : whole_launch_two<kUpperMatvec, false, true>(false, a, M, grid, smem, set_attr, s);
-            case kLowerSolve: return whole_launch_two<kLowerSolve, false, true>(false, a, M, grid, smem, set_attr, s);
-            default: return cudaErrorInvalidValue;
-        }
+        if (mode != kLowerMatvec) return cudaErrorInvalidValue;  // a measured alternative, kept for the lower mat-vec only
+        return fma ? whole_launch_two<kLowerMatvec, true, true>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, true>(timeline, a, M, grid, smem, set_attr, s);
     }
-    // 4-row blocks exist for the lower mat-vec (fnt / ifnt); every other mode folds two rows
+    (void)rows;  // every mode folds two rows side by side (four-row blocks lost to the two-fibre forms and were removed)
     switch (mode) {
         case kLowerMatvec:
-            if (rows == 4) return fma ? whole_launch_tg<kLowerMatvec, true, 4>(threads, timeline, a, M, grid, smem, set_attr, s) : whole_launch_tg<kLowerMatvec, false, 4>(threads, timeline, a, M, grid, smem, set_attr, s);
             return fma ? whole_launch_tg<kLowerMatvec, true, 2>(threads, timeline, a, M, grid, smem, set_attr, s) : whole_launch_tg<kLowerMatvec, false, 2>(threads, timeline, a, M, grid, smem, set_attr, s);
         case kUpperMatvec: return fma ? whole_launch_tg<kUpperMatvec, true, 2>(threads, false, a, M, grid, smem, set_attr, s) : whole_launch_tg<kUpperMatvec, false, 2>(threads, false, a, M, grid, smem, set_attr, s);
         case kLowerSolve: return whole_launch_tg<kLowerSolve, false, 2>(threads, false, a, M, grid, smem, set_attr, s);

@@ -409,8 +409,7 @@ def test_eval_few_points_split_path(T, m, n, p, P):
     {"use_whole": 0},
     {"use_whole": 1},
     {"use_whole": 1, "whole_threads": 384},
-    {"use_whole": 1, "whole_threads": 768, "whole_rows": 4},
-    {"use_whole": 1, "whole_threads": 384, "whole_order": 0, "whole_rows": 2},
+    {"use_whole": 1, "whole_threads": 384, "whole_order": 0},
     {"use_whole": 1, "whole_order": 63},
     {"use_whole": 1, "whole_threads": 384, "whole_fibres": 2},
     {"use_whole": 1, "whole_threads": 384, "whole_fibres": 2, "whole_order": 0},
@@ -426,7 +425,7 @@ def test_eval_few_points_split_path(T, m, n, p, P):
 @pytest.mark.parametrize("name", ["c2_d3n20_leja", "d4n8", "d5n6", "d6n4", "d2n7_inf", "d3n12_solve", "c4_d3n30"])
 def test_alternative_kernel_families(T, name, opts):
     """The selectable kernel paths (per-coordinate kernels, slab kernel, whole-function kernel
-    with 384 or 768 threads per CTA, 2- or 4-row blocks, other item orders) must all reproduce the reference bit for bit."""
+    with 384 or 768 threads per CTA, one or two fibres per thread, other item orders) must all reproduce the reference bit for bit."""
     g = load_case(name)
     t = make(T, g, exact_ifnt=True)
     for k, v in opts.items():
