@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "liblpfnt.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xfatbin=-compress-all", "-Xcompiler", "-fPIC"]
 
 # (source, object name, extra defines)
 UNITS = [
