@@ -1,5 +1,5 @@
 set -x
-python -m pytest tests -m gpu -x -q -k "golden or alternative or property or generic or c3" 2>&1 | tail -3
-for o in 1 2 0; do python tools/quick.py --m 6 --n 20 --batch 1 --iters 20 --flush --check 0 --opt use_cta_cap=$o; done
-python tools/quick.py --m 4 --n 20 --batch 64 --iters 20 --check 0 --opt use_cta_cap=1 --trace 0
-python tools/quick.py --m 4 --n 20 --batch 64 --iters 20 --check 0 --opt use_cta_cap=2 --trace 0
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --opt whole_threads_exact=640 --opt whole_fibres_exact=1
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --opt whole_threads_exact=640 --opt whole_fibres_exact=1 --sweep whole_order_exact=40,104,36,100,0,64
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --sweep whole_order_exact=104
+python tools/timeline.py 30 whole_threads_exact=640 whole_fibres_exact=1 > gpurun_out/timeline_r2i.txt 2>&1; grep -E "==|period|warp  0|warp 19|warp 10" gpurun_out/timeline_r2i.txt | head -12
