@@ -159,7 +159,9 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          "use_slab" (coordinates 0 and 1 in one pass over slabs of planes, any m >= 2: 1 = when the slabs
  *          fill the CTA (default), 0 = off, 2 = always), "use_cta_cap" (k_sweep_groups: per-CTA row capacity),
  *          "eval_block" (0 = non-staged eval kernel), "timeline" (development: clock64 stamps of the
- *          whole-function kernel), "host_chunk_bytes" (host-pointer calls: bytes per pipelined chunk, 0 = automatic).
+ *          whole-function kernel), "host_chunk_bytes" (host-pointer calls: bytes per pipelined chunk, 0 = automatic),
+ *          "host_threads" (host-pointer calls on PAGEABLE memory: threads that copy the chunks to / from the plan's pinned
+ *          staging buffers; 0 = automatic, 1 = single-threaded), "eval_split" (eval of few points: -1 automatic, 0 off, 1 on).
  * A plan owns one set of workspaces: use it from one host thread and one stream at a time. */
 int lpfnt_plan_set_option(lpfnt_plan *plan, const char *name, int64_t value);
 /* Drain the trace: per recorded launch a label (100 * kernel kind + coordinate; kinds: 0 line

@@ -547,6 +547,37 @@ def eval_truth_longdouble(c, nodes, pts, A):
     return out
 
 
+@pytest.mark.parametrize("chunk_bytes,threads", [(1 << 20, 0), (1 << 20, 1), (3 << 20, 3), (0, 0)])
+def test_pageable_host_arrays_are_staged(T, chunk_bytes, threads):
+    """Plain (pageable) NumPy arrays of >= 4 MB go through the plan's pinned staging buffers, copied by host threads while
+    the other lane's chunk is on the GPU; the result must equal the pinned-buffer path bit for bit, for every chunking."""
+    from lpfun_b200 import _native as nat
+
+    g = load_case("c4_d3n30")
+    t = make(T, g, exact_ifnt=True)
+    N = len(t)
+    B = 67  # 8.2 MB: odd number of functions, last chunk partial
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((B, N))
+    hv = nat.pinned_empty((B, N)); hc = nat.pinned_empty((B, N)); hr = nat.pinned_empty((B, N))
+    hv[:] = v
+    t.fnt(hv, out=hc); t.ifnt(hc, out=hr)
+    t.set_option("host_chunk_bytes", chunk_bytes)
+    t.set_option("host_threads", threads)
+    c = t.fnt(v)           # pageable in, fresh pageable out
+    assert np.array_equal(c, hc)
+    r = t.ifnt(c)
+    assert np.array_equal(r, hr)
+    out = np.empty_like(v)
+    t.fnt(hv, out=out)     # pinned in, pageable out
+    assert np.array_equal(out, hc)
+    t.ifnt(c, out=hr)      # pageable in, pinned out
+    assert np.array_equal(hr, r)
+    for a in (hv, hc, hr):
+        nat.pinned_free(a)
+    t.close()
+
+
 def test_batch_beyond_the_grid_limit(T):
     """More functions than gridDim.y allows in one launch (65 535): the launchers loop."""
     from oracle import oracle as O

@@ -1,5 +1,23 @@
 set -x
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --opt whole_threads_exact=640 --opt whole_fibres_exact=1
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --opt whole_threads_exact=640 --opt whole_fibres_exact=1 --sweep whole_order_exact=40,104,36,100,0,64
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --sweep whole_order_exact=104
-python tools/timeline.py 30 whole_threads_exact=640 whole_fibres_exact=1 > gpurun_out/timeline_r2i.txt 2>&1; grep -E "==|period|warp  0|warp 19|warp 10" gpurun_out/timeline_r2i.txt | head -12
+python -m pytest tests -m gpu -x -q -k "pageable or golden or device_tensor" 2>&1 | tail -3
+python - <<'PY'
+import numpy as np, time, lpfun_b200
+t = lpfun_b200.Transform(3, 30, report=False)
+N = len(t)
+for B in (1024, 4096):
+    v = np.random.default_rng(0).standard_normal((B, N))
+    for thr in (0, 1, 2, 4, 6, 8):
+        t.set_option("host_threads", thr)
+        r = t.ifnt(t.fnt(v))
+        t0 = time.perf_counter()
+        for _ in range(2): r = t.ifnt(t.fnt(v))
+        dt = (time.perf_counter() - t0) / 2
+        print(f"pageable B={B} host_threads={thr}: {dt*1e3:.1f} ms per round trip = {2*N*B/dt/1e9:.2f} GDOF/s", flush=True)
+    out = np.empty_like(v); out2 = np.empty_like(v)
+    t.set_option("host_threads", 0)
+    t.fnt(v, out=out); t.ifnt(out, out=out2)
+    t0 = time.perf_counter()
+    for _ in range(2): t.fnt(v, out=out); t.ifnt(out, out=out2)
+    dt = (time.perf_counter() - t0) / 2
+    print(f"pageable B={B} preallocated outputs: {dt*1e3:.1f} ms = {2*N*B/dt/1e9:.2f} GDOF/s", flush=True)
+PY
