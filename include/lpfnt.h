@@ -101,7 +101,9 @@ enum {
                                    thread order: bits 0..15 line offset (coordinate 0) / first entry in WHOLE_SEO,
                                    bits 16..21 length, bits 22..31 lane a_0                                      */
     LPFNT_TAB_WHOLE_SEO = 11,   /* uint16: per coordinate h >= 1 the line offsets in fibre order                */
-    LPFNT_TAB_LINE_LAST = 12    /* N_1 uint8: a_{m-1} of every line                                    */
+    LPFNT_TAB_LINE_LAST = 12,   /* N_1 uint8: a_{m-1} of every line                                    */
+    LPFNT_TAB_WSPLIT_ITEMS = 13, /* uint32: item lists of the split whole-function kernel (two parts x three coordinates)  */
+    LPFNT_TAB_WSPLIT_SEO = 14    /* uint16: its row offsets (inside the part)                                                */
 };
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);
@@ -113,6 +115,12 @@ int lpfnt_index_destroy(lpfnt_index *index);
  * longest item, most items of a list, {list offset, padded list length} per coordinate; returns the number written. */
 int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order, int fibres);
 int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta);
+/* Split whole-function kernel (m = 3): the function as two units, planes a_2 < C and a_2 >= C (C <= 0: balanced), so that two
+ * CTAs fit on an SM.  Meta: 83 int32 = ok, C, {e0, ne} x 2 parts, {list offset, padded length} x 2 parts x 3 coordinates, number of
+ * columns of part Q, cb[32], rq[32] (column (a_0, a_1) of Q = cb[a_1] + a_0 for a_0 < rq[a_1]).  Item word: bits 0..15 line offset
+ * inside the part / first entry in WSPLIT_SEO, 16..21 length, 22..26 lane a_0, 27..31 plane a_2 (coordinate 1) / row a_1 (coordinate 2). */
+int lpfnt_index_wsplit_build(lpfnt_index *index, int C, int order);
+int lpfnt_index_wsplit_meta(const lpfnt_index *index, int32_t *meta);
 int64_t lpfnt_index_size(const lpfnt_index *index, int what, int h);
 int lpfnt_index_copy(const lpfnt_index *index, int what, int h, void *dst);
 
@@ -156,6 +164,9 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          1 item per thread, 2 = two of equal length class folded side by side, 3 = a long and a short one folded one
  *          after the other; item order, see lpfnt_index_whole_build; -1 = automatic; the suffixes "_exact" / "_fma"
  *          address the tables of the exact / the fused-multiply-add forms only),
+ *          "whole_split" (m = 3: every function as two units -- planes a_2 < C and a_2 >= C -- so that two CTAs fit on an SM;
+ *          0 = off (default: measured slower), 1 = on, -1 = automatic), "whole_split_c" (the split plane, 0 = balanced),
+ *          "whole_split_order", "whole_split_skew" (cycles the second CTA of an SM starts late),
  *          "use_slab" (coordinates 0 and 1 in one pass over slabs of planes, any m >= 2: 1 = when the slabs
  *          fill the CTA (default), 0 = off, 2 = always), "use_cta_cap" (k_sweep_groups: per-CTA row capacity),
  *          "eval_block" (0 = non-staged eval kernel), "timeline" (development: clock64 stamps of the

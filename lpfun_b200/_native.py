@@ -42,6 +42,8 @@ def _declare(L):
     L.lpfnt_index_copy.argtypes = [vp, i32, i32, vp]
     L.lpfnt_index_whole_build.argtypes = [vp, i32, i32, i32]
     L.lpfnt_index_whole_meta.argtypes = [vp, vp]
+    L.lpfnt_index_wsplit_build.argtypes = [vp, i32, i32]
+    L.lpfnt_index_wsplit_meta.argtypes = [vp, vp]
     L.lpfnt_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.lpfnt_host_free.argtypes = [vp]
     L.lpfnt_plan_create.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(vp)]
@@ -130,9 +132,9 @@ def pinned_free(arr: np.ndarray):
 
 
 (TAB_LINE_OFF, TAB_FIB_PTR, TAB_FIB_ENT, TAB_THR_START, TAB_THR_FIB, TAB_LINE_ALPHA, TAB_LEVEL_SIZE,
- TAB_GROUPS, TAB_LINE_ORDER, TAB_GROUP_T, TAB_WHOLE_ITEMS, TAB_WHOLE_SEO, TAB_LINE_LAST) = range(13)
+ TAB_GROUPS, TAB_LINE_ORDER, TAB_GROUP_T, TAB_WHOLE_ITEMS, TAB_WHOLE_SEO, TAB_LINE_LAST, TAB_WSPLIT_ITEMS, TAB_WSPLIT_SEO) = range(15)
 _TAB_DTYPE = {TAB_LINE_ALPHA: np.uint8, TAB_LEVEL_SIZE: np.int64, TAB_GROUP_T: np.uint8, TAB_WHOLE_SEO: np.uint16, TAB_LINE_LAST: np.uint8,
-              TAB_WHOLE_ITEMS: np.uint32}
+              TAB_WHOLE_ITEMS: np.uint32, TAB_WSPLIT_ITEMS: np.uint32, TAB_WSPLIT_SEO: np.uint16}
 
 
 class IndexTables:
@@ -155,6 +157,21 @@ class IndexTables:
 
     def whole_build(self, threads: int = 768, order: int = -1, fibres: int = 1):
         check(lib().lpfnt_index_whole_build(self._h, int(threads), int(order), int(fibres)))
+
+    def wsplit_build(self, C: int = 0, order: int = -1):
+        check(lib().lpfnt_index_wsplit_build(self._h, int(C), int(order)))
+
+    def wsplit_meta(self) -> dict:
+        meta = np.zeros(83, dtype=np.int32)
+        lib().lpfnt_index_wsplit_meta(self._h, meta.ctypes.data)
+        d = {"ok": int(meta[0]), "C": int(meta[1]), "e0": meta[[2, 4]].tolist(), "ne": meta[[3, 5]].tolist()}
+        lists = meta[6:18].reshape(2, 3, 2)
+        d["item_off"] = lists[:, :, 0].tolist()
+        d["n_items"] = lists[:, :, 1].tolist()
+        d["ncolq"] = int(meta[18])
+        d["cb"] = meta[19:51].tolist()
+        d["rq"] = meta[51:83].tolist()
+        return d
 
     def whole_meta(self) -> dict:
         meta = np.zeros(10, dtype=np.int32)

@@ -106,6 +106,17 @@ struct lpfnt_plan {
     } whole[2];
     struct WholeCfg { int threads = -1, fibres = -1, order = kWholeDefaultOrder, rows = -1; } wcfg[2];
     uint16_t *d_perm16 = nullptr;
+    // split whole-function kernel (two units per function, two CTAs per SM; m = 3, lower mat-vec)
+    struct WholeSplit {
+        WholeSplitHost h;                    // host copy (items / seo dropped after the upload)
+        uint32_t *d_items = nullptr;
+        uint16_t *d_seo = nullptr;
+        double *d_scratch = nullptr;
+        int32_t total_items = 0, seo_len = 0, buf_elems = 0;
+        size_t smem_bytes = 0;
+    } wsplit;
+    int use_whole_split = 0;                 // 0 off (default: measured slower), 1 whenever the tables exist, -1 automatic
+    int whole_split_c = 0, whole_split_order = kWholeDefaultOrder, whole_split_skew = 0;
     std::bitset<512> whole_attr_set;         // per kernel instantiation: dynamic shared memory opted in on this device
     int use_whole = -1;                      // -1 auto (batches of >= 8 functions), 0 off, 1 always
     HostIndex *hx = nullptr;                 // kept for plans that can run the whole-function kernel (re-build of its tables)
@@ -487,6 +498,106 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     return LPFNT_OK;
 }
 
+
+// ---- split whole-function kernel (k_whole_split) ----
+void free_wsplit(lpfnt_plan *p) {
+    lpfnt_plan::WholeSplit &W = p->wsplit;
+    cudaFree(W.d_items); cudaFree(W.d_seo); cudaFree(W.d_scratch);
+    W.d_items = nullptr; W.d_seo = nullptr; W.d_scratch = nullptr;
+    W.h = WholeSplitHost();
+}
+
+int upload_wsplit(lpfnt_plan *p) {
+    lpfnt_plan::WholeSplit &W = p->wsplit;
+    free_wsplit(p);
+    if (!p->hx || p->m != 3) return LPFNT_OK;
+    // the split plane: as given, else the one for which the larger part is smallest among those that fit twice into an SM
+    int best_c = 0;
+    if (p->whole_split_c > 0) best_c = p->whole_split_c;
+    else {
+        int64_t best = -1;
+        for (int c = 1; c <= 16; ++c) {
+            p->hx->build_whole_split(c, p->whole_split_order);
+            const WholeSplitHost &h = p->hx->wsplit;
+            if (!h.ok) continue;
+            const int be = (std::max(h.ne[0], h.ne[1]) + 5) & ~1;
+            const size_t sm = whole_split_smem_bytes(be, int(h.items.size()), int(h.seo.size()), int(p->N), p->has_perm);
+            if (sm > size_t(kWholeSmemPerCta)) continue;
+            // prefer one round per sweep for coordinates 0 and 1, then the smaller buffer
+            const int64_t score = int64_t(h.n_items[0][0] + h.n_items[0][1] + h.n_items[1][0] + h.n_items[1][1]) * 100000 + be;
+            if (best < 0 || score < best) { best = score; best_c = c; }
+        }
+    }
+    if (best_c <= 0) return LPFNT_OK;
+    p->hx->build_whole_split(best_c, p->whole_split_order);
+    if (!p->hx->wsplit.ok) return LPFNT_OK;
+    W.h = p->hx->wsplit;
+    W.buf_elems = (std::max(W.h.ne[0], W.h.ne[1]) + 5) & ~1;
+    W.smem_bytes = whole_split_smem_bytes(W.buf_elems, int(W.h.items.size()), int(W.h.seo.size()), int(p->N), p->has_perm);
+    if (W.smem_bytes > size_t(kWholeSmemPerCta)) { W.h = WholeSplitHost(); return LPFNT_OK; }
+    int rc;
+    if ((rc = upload(&W.d_items, W.h.items.data(), W.h.items.size(), p))) return rc;
+    if ((rc = upload(&W.d_seo, W.h.seo.data(), W.h.seo.size(), p))) return rc;
+    const size_t sc = size_t(2) * p->num_sms * size_t(W.h.C) * size_t(std::max(W.h.ncolq, 1));
+    CK(cudaMalloc(reinterpret_cast<void **>(&W.d_scratch), sc * sizeof(double)));
+    p->table_bytes += int64_t(sc * sizeof(double));
+    W.total_items = int32_t(W.h.items.size());
+    W.seo_len = int32_t(W.h.seo.size());
+    W.h.items.clear(); W.h.items.shrink_to_fit();
+    W.h.seo.clear(); W.h.seo.shrink_to_fit();
+    return LPFNT_OK;
+}
+
+bool wsplit_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dims, const double *in, int64_t batch) {
+    const lpfnt_plan::WholeSplit &W = p->wsplit;
+    if (!W.h.ok || p->force_generic || p->use_whole == 0 || p->use_whole_split == 0 || int(dims.size()) != 3) return false;
+    for (int q = 0; q < 3; ++q) if (dims[q] != q) return false;
+    if (sweep_mode(spec) != kLowerMatvec) return false;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return false;
+    if (pick_cap(std::max(W.h.max_t, 1)) < 24) return false;  // small functions fit twice into an SM unsplit
+    // automatic: only when the unsplit kernel is limited to one CTA per SM, and for batches that fill the GPU
+    if (p->use_whole_split == 1) return true;
+    const lpfnt_plan::Whole &U = p->whole[spec.fma ? 1 : 0];
+    const bool unsplit_two_ctas = U.h.ok && U.h.threads == 384 && U.h.fibres == 1 && U.smem_bytes <= size_t(kWholeSmemPerCta);
+    return p->use_whole_split == -1 && p->use_whole != 0 && !unsplit_two_ctas && batch >= 2 * p->num_sms;
+}
+
+int launch_wsplit_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, double *dst, int64_t batch, bool gather, bool scatter, cudaStream_t s) {
+    lpfnt_plan::WholeSplit &W = p->wsplit;
+    const int cap = pick_cap(std::max(W.h.max_t, 1));
+    const double *tri = operator_tri(p, spec.op, cap);
+    WholeSplitArgs a{};
+    a.items = W.d_items; a.seo = W.d_seo; a.perm16 = p->d_perm16; a.scratch = W.d_scratch;
+    a.dbg = p->d_timeline;
+    for (int q = 0; q < 2; ++q) {
+        a.e0[q] = W.h.e0[q]; a.ne[q] = W.h.ne[q];
+        for (int h = 0; h < 3; ++h) { a.item_off[q][h] = W.h.item_off[q][h]; a.n_items[q][h] = W.h.n_items[q][h]; }
+    }
+    for (int q = 0; q < 32; ++q) { a.cb[q] = W.h.cb[q]; a.rq[q] = W.h.rq[q]; }
+    a.total_items = W.total_items; a.seo_len = W.seo_len; a.ncolq = std::max(W.h.ncolq, 1); a.C = W.h.C;
+    a.buf_elems = W.buf_elems;
+    a.gather = gather ? 1 : 0; a.scatter = scatter ? 1 : 0;
+    a.n_elem = int32_t(p->N);
+    a.skew = p->whole_split_skew;
+    const bool timeline = p->d_timeline != nullptr;
+    const int key = 400 + (cap == 32 ? 0 : 4) + (spec.fma ? 1 : 0) + (timeline ? 2 : 0);
+    const bool set_attr = !p->whole_attr_set[key];
+    for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
+        const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
+        a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
+        const int grid = int(std::min<int64_t>(nb, int64_t(2) * p->num_sms));
+        cudaError_t e = cudaSuccess;
+        trace_begin(p, 1500, s);
+        if (cap == 32) e = launch_whole_split<32>(spec.fma, timeline, a, tri, grid, W.smem_bytes, set_attr, s);
+        else e = launch_whole_split<24>(spec.fma, timeline, a, tri, grid, W.smem_bytes, set_attr, s);
+        trace_end(p, s);
+        p->launches += 1;
+        if (e != cudaSuccess) { set_error(std::string("split whole-function kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+        p->whole_attr_set[key] = true;
+    }
+    return LPFNT_OK;
+}
+
 // Device-resident pipeline: sweeps along `dims` (ascending), optional colex gather on the way
 // in and scatter on the way out.  in/out may alias.
 //
@@ -501,6 +612,7 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     scatter = scatter && p->has_perm;
     if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
+    if (wsplit_ok(p, spec, dims, in, batch)) return launch_wsplit_fn(p, spec, in, out, batch, gather, scatter, s);
     if (whole_ok(p, spec, dims, in, batch)) {
         // in-place is safe: a function is complete in shared memory / registers before its first store
         return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s);
@@ -806,6 +918,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         }
         for (int which = 0; which < 2; ++which)
             if ((rc = upload_whole(p, which))) return fail(rc);
+        if ((rc = upload_wsplit(p))) return fail(rc);
     }
     if (!hx.eval_block.empty()) {
         static_assert(sizeof(EvalBlock) == sizeof(int4), "EvalBlock must match int4");
@@ -841,6 +954,7 @@ int lpfnt_plan_destroy(lpfnt_plan *p) {
     for (auto &es : p->eval_splits) { cudaFree(es.d_l0); cudaFree(es.d_alpha); }
     free_whole(p, 0);
     free_whole(p, 1);
+    free_wsplit(p);
     cudaFree(p->d_perm16);
     delete p->hx;
     cudaFree(p->d_timeline);
@@ -895,6 +1009,15 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
         return LPFNT_OK;
     }
     if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
+    if (std::strcmp(name, "whole_split_skew") == 0) { p->whole_split_skew = int(std::max<int64_t>(0, std::min<int64_t>(value, 1000000))); return LPFNT_OK; }
+    if (std::strcmp(name, "whole_split") == 0) { p->use_whole_split = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
+    if (std::strcmp(name, "whole_split_c") == 0 || std::strcmp(name, "whole_split_order") == 0) {
+        if (name[12] == 'c') p->whole_split_c = int(std::max<int64_t>(0, std::min<int64_t>(value, 16)));
+        else p->whole_split_order = value < 0 ? kWholeDefaultOrder : int(value & 127);
+        CK(cudaSetDevice(p->device));
+        CK(cudaDeviceSynchronize());
+        return upload_wsplit(p);
+    }
     if (std::strncmp(name, "whole_", 6) == 0) {
         // whole_<threads|fibres|order|rows>[_exact|_fma]: CTA shape of the whole-function kernel, for both forms or one
         std::string key(name + 6);

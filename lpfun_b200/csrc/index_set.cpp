@@ -348,6 +348,84 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
     return true;
 }
 
+namespace {
+struct WholeItem { int t; uint32_t w; };
+
+// Orders the items of one sweep (length classes, natural order inside a class) and appends them to `out` in THREAD order:
+// rounds of TG * NF slots, thread i owning slots i, TG + i; inside a round chunks of 32 items dealt to the warps.
+// Returns the padded list length.
+int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool model, int TG, int NF, bool seq, std::vector<uint32_t> &out) {
+    const int RT = TG * NF;
+    const int cls[4] = {1, 8, 16, 1 << 20};
+    const int q = cls[order_code & 3];
+    std::stable_sort(nat.begin(), nat.end(), [q](const WholeItem &a, const WholeItem &b) { return (a.t + q - 1) / q > (b.t + q - 1) / q; });
+    const int32_t nit = int32_t(nat.size()), padded = int32_t((nit + RT - 1) / RT) * RT;
+    const int nw = TG / 32, CH = seq ? 32 : 32 * NF;
+    for (int32_t r0 = 0; r0 < padded; r0 += RT) {
+        // chunks of CH items (longest first); warp w runs on SM sub-partition w % 4
+        const int nch = RT / CH;
+        std::vector<double> wgt(nch, 0.0);
+        for (int c = 0; c < nch; ++c) {
+            int tm = 0;
+            for (int i = 0; i < CH; ++i) { const int32_t src = r0 + c * CH + i; if (src < nit) tm = std::max(tm, nat[src].t); }
+            const int tt = (tm + 1) & ~1;
+            wgt[c] = 0.5 * tt * (tt + 1);
+        }
+        // a warp's unit of work: one chunk, or (seq) the LONG chunk c together with the SHORT chunk nch - 1 - c -- the
+        // work of an item is quadratic in its length, so the sums come out nearly equal
+        std::vector<double> unit(nw, 0.0);
+        for (int c = 0; c < nw; ++c) unit[c] = seq ? wgt[c] + wgt[nch - 1 - c] : wgt[c];
+        std::vector<int> warp_of(nw);  // unit -> warp
+        // start: SNAKE order over the four sub-partitions (0 1 2 3 / 3 2 1 0 / ...): equal sums of work
+        for (int c = 0; c < nw; ++c) { const int grp = c >> 2; warp_of[c] = grp * 4 + ((grp & 1) ? 3 - (c & 3) : (c & 3)); }
+        if (model) {
+            // The FP64 pipe of a sub-partition is shared by its warps, and one or two warps alone cannot keep it busy
+            // (tools/probe5.cu: equal sums but unequal chunks cost 17-25 % of a sweep): the sweep ends when the
+            // sub-partition whose longest unit outlasts its other units by most is done.  Model: processor sharing
+            // with rate r(j) of the pipe while j warps are still computing; hill-climb over swaps.
+            const double r1 = NF == 2 ? 0.70 : 0.45, r2 = NF == 2 ? 0.88 : 0.75, r3 = NF == 2 ? 0.93 : 0.90, r4 = 0.93;
+            auto part_time = [&](int sp) {
+                double a[64]; int k = 0;
+                for (int c = 0; c < nw; ++c) if ((warp_of[c] & 3) == sp && unit[c] > 0) a[k++] = unit[c];
+                std::sort(a, a + k);  // ascending: a[0] finishes first
+                double tsum = 0, prev = 0;
+                for (int i = 0; i < k; ++i) {
+                    const int act = k - i;
+                    const double r = act == 1 ? r1 : act == 2 ? r2 : act == 3 ? r3 : r4;
+                    tsum += (a[i] - prev) * act / r;
+                    prev = a[i];
+                }
+                return tsum;
+            };
+            auto cost = [&]() { double mx = 0, sm = 0; for (int sp = 0; sp < 4; ++sp) { const double t = part_time(sp); mx = std::max(mx, t); sm += t; } return mx + 1e-3 * sm; };
+            double best = cost();
+            for (bool improved = true; improved;) {
+                improved = false;
+                for (int c1 = 0; c1 < nw; ++c1)
+                    for (int c2 = c1 + 1; c2 < nw; ++c2) {
+                        if ((warp_of[c1] & 3) == (warp_of[c2] & 3)) continue;
+                        std::swap(warp_of[c1], warp_of[c2]);
+                        const double t = cost();
+                        if (t < best - 1e-9) { best = t; improved = true; }
+                        else std::swap(warp_of[c1], warp_of[c2]);
+                    }
+            }
+        }
+        std::vector<int> unit_of(nw);
+        for (int c = 0; c < nw; ++c) unit_of[warp_of[c]] = c;
+        for (int slot = 0; slot < RT; ++slot) {
+            // side by side: lane l of the warp owns items l and 32 + l of its chunk (neighbours in the length order)
+            const int f = slot / TG, tid = slot % TG;
+            const int u = unit_of[tid >> 5];
+            const int32_t src = seq ? r0 + (f == 0 ? u : nch - 1 - u) * 32 + (tid & 31) : r0 + u * CH + f * 32 + (tid & 31);
+            out.push_back(src < nit ? nat[src].w : 0u);
+        }
+    }
+    return padded;
+}
+}  // namespace
+
+
 void HostIndex::build_whole(int threads, int order, int fibres) {
     whole = WholeHost();
     WholeHost &W = whole;
@@ -377,9 +455,8 @@ void HostIndex::build_whole(int threads, int order, int fibres) {
     }
     for (int q = 0; q < kMaxRegT + 8 || W.seo.size() % 8; ++q) W.seo.push_back(0);
     if (W.seo.size() > 65536) return;
-    struct Item { int t; uint32_t w; };
     for (int h = 0; h < m; ++h) {
-        std::vector<Item> nat;
+        std::vector<WholeItem> nat;
         if (h == 0) {
             for (int64_t l = 0; l < N1; ++l) {
                 const int t = line_off[l + 1] - line_off[l];
@@ -397,76 +474,118 @@ void HostIndex::build_whole(int threads, int order, int fibres) {
                 }
             }
         }
-        const int cls[4] = {1, 8, 16, 1 << 20};
-        const int q = cls[(order >> (2 * h)) & 3];
-        std::stable_sort(nat.begin(), nat.end(), [q](const Item &a, const Item &b) { return (a.t + q - 1) / q > (b.t + q - 1) / q; });
-        for (const Item &it : nat) W.max_t = std::max(W.max_t, it.t);
-        const int32_t nit = int32_t(nat.size()), padded = rounds(nit);
+        const int32_t nit = int32_t(nat.size());
+        for (const WholeItem &it : nat) W.max_t = std::max(W.max_t, it.t);
         W.item_off[h] = int32_t(W.items.size());
-        W.n_items[h] = padded;
+        W.n_items[h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, NF, seq, W.items);
         W.max_items = std::max(W.max_items, nit);
-        const int nw = TG / 32, CH = seq ? 32 : 32 * NF;
-        for (int32_t r0 = 0; r0 < padded; r0 += RT) {
-            // chunks of CH items (longest first); warp w runs on SM sub-partition w % 4
-            const int nch = RT / CH;
-            std::vector<double> wgt(nch, 0.0);
-            for (int c = 0; c < nch; ++c) {
-                int tm = 0;
-                for (int i = 0; i < CH; ++i) { const int32_t src = r0 + c * CH + i; if (src < nit) tm = std::max(tm, nat[src].t); }
-                const int tt = (tm + 1) & ~1;
-                wgt[c] = 0.5 * tt * (tt + 1);
-            }
-            // a warp's unit of work: one chunk, or (seq) the LONG chunk c together with the SHORT chunk nch - 1 - c -- the
-            // work of an item is quadratic in its length, so the sums come out nearly equal
-            std::vector<double> unit(nw, 0.0);
-            for (int c = 0; c < nw; ++c) unit[c] = seq ? wgt[c] + wgt[nch - 1 - c] : wgt[c];
-            std::vector<int> warp_of(nw);  // unit -> warp
-            // start: SNAKE order over the four sub-partitions (0 1 2 3 / 3 2 1 0 / ...): equal sums of work
-            for (int c = 0; c < nw; ++c) { const int grp = c >> 2; warp_of[c] = grp * 4 + ((grp & 1) ? 3 - (c & 3) : (c & 3)); }
-            if (order & 64) {
-                // The FP64 pipe of a sub-partition is shared by its warps, and one or two warps alone cannot keep it busy
-                // (tools/probe5.cu: equal sums but unequal chunks cost 17-25 % of a sweep): the sweep ends when the
-                // sub-partition whose longest unit outlasts its other units by most is done.  Model: processor sharing
-                // with rate r(j) of the pipe while j warps are still computing; hill-climb over swaps.
-                const double r1 = NF == 2 ? 0.70 : 0.45, r2 = NF == 2 ? 0.88 : 0.75, r3 = NF == 2 ? 0.93 : 0.90, r4 = 0.93;
-                auto part_time = [&](int sp) {
-                    double a[64]; int k = 0;
-                    for (int c = 0; c < nw; ++c) if ((warp_of[c] & 3) == sp && unit[c] > 0) a[k++] = unit[c];
-                    std::sort(a, a + k);  // ascending: a[0] finishes first
-                    double tsum = 0, prev = 0;
-                    for (int i = 0; i < k; ++i) {
-                        const int act = k - i;
-                        const double r = act == 1 ? r1 : act == 2 ? r2 : act == 3 ? r3 : r4;
-                        tsum += (a[i] - prev) * act / r;
-                        prev = a[i];
-                    }
-                    return tsum;
-                };
-                auto cost = [&]() { double mx = 0, sm = 0; for (int sp = 0; sp < 4; ++sp) { const double t = part_time(sp); mx = std::max(mx, t); sm += t; } return mx + 1e-3 * sm; };
-                double best = cost();
-                for (bool improved = true; improved;) {
-                    improved = false;
-                    for (int c1 = 0; c1 < nw; ++c1)
-                        for (int c2 = c1 + 1; c2 < nw; ++c2) {
-                            if ((warp_of[c1] & 3) == (warp_of[c2] & 3)) continue;
-                            std::swap(warp_of[c1], warp_of[c2]);
-                            const double t = cost();
-                            if (t < best - 1e-9) { best = t; improved = true; }
-                            else std::swap(warp_of[c1], warp_of[c2]);
-                        }
-                }
-            }
-            std::vector<int> unit_of(nw);
-            for (int c = 0; c < nw; ++c) unit_of[warp_of[c]] = c;
-            for (int slot = 0; slot < RT; ++slot) {
-                // side by side: lane l of the warp owns items l and 32 + l of its chunk (neighbours in the length order)
-                const int f = slot / TG, tid = slot % TG;
-                const int u = unit_of[tid >> 5];
-                const int32_t src = seq ? r0 + (f == 0 ? u : nch - 1 - u) * 32 + (tid & 31) : r0 + u * CH + f * 32 + (tid & 31);
-                W.items.push_back(src < nit ? nat[src].w : 0u);
-            }
+    }
+    W.ok = true;
+}
+
+// Tables of the split whole-function kernel (k_whole_split, m = 3): the function is processed as two units,
+//   part P = planes a_2 <  C  (elements [0, e0[1]): contiguous), part Q = planes a_2 >= C,
+// so that TWO CTAs fit on an SM.  Coordinates 0 and 1 never couple different planes and run inside each part.  The last
+// coordinate: unit P folds the rows k < C of every column (a_0, a_1); unit Q folds the rows k >= C of the columns that
+// reach beyond C from the very first term -- the values y[j], j < C, it needs come from unit P's coordinate-1 results,
+// exported to a scratch buffer [a_2][column] in global memory (columns of Q numbered a_1-major: cb[a_1] + a_0, a_0 < rq[a_1]).
+// Item word: bits 0..15 line offset inside the part (coordinate 0) / first seo entry, 16..21 length, 22..26 lane a_0,
+// 27..31 the plane a_2 (coordinate 1) / the row a_1 (coordinate 2).
+void HostIndex::build_whole_split(int C, int order) {
+    wsplit = WholeSplitHost();
+    WholeSplitHost &W = wsplit;
+    if (m != 3 || N >= 65536 || max_line > kMaxRegT || n + 1 > kMaxRegT || line_alpha.empty()) return;
+    for (int h = 1; h < m; ++h)
+        if (dims[h].max_lines > kMaxRegT) return;
+    const int n1 = n + 1;
+    auto A1 = [&](int64_t l) { return int(line_alpha[l * 2]); };
+    auto A2 = [&](int64_t l) { return int(line_alpha[l * 2 + 1]); };
+    auto LEN = [&](int64_t l) { return line_off[l + 1] - line_off[l]; };
+    // lines of a plane are consecutive (colex) with a_1 ascending from 0; planes ascending in a_2
+    std::vector<int64_t> plane0(n1 + 1, N1);  // first line of every plane
+    int planes = 0;
+    for (int64_t l = 0; l < N1; ++l) {
+        if (A1(l) == 0) { if (A2(l) != planes) return; plane0[planes++] = l; }
+        else if (l == 0 || A2(l) != A2(l - 1) || A1(l) != A1(l - 1) + 1) return;
+    }
+    plane0[planes] = N1;
+    if (C <= 0) {  // automatic: the split that balances the two parts
+        int64_t best = -1;
+        for (int c = 1; c < planes; ++c) {
+            const int64_t eP = line_off[plane0[c]], big = std::max<int64_t>(eP, N - eP);
+            if (best < 0 || big < best) { best = big; C = c; }
         }
     }
+    if (C < 1 || C >= planes || C > 16) return;
+    W.C = C;
+    const int64_t LP = plane0[C];
+    W.e0[0] = 0; W.ne[0] = line_off[LP];
+    W.e0[1] = line_off[LP]; W.ne[1] = int32_t(N - line_off[LP]);
+    // line (a_1, a_2) -> line index (or -1)
+    auto line_of = [&](int a1, int a2) -> int64_t {
+        if (a2 >= planes) return -1;
+        const int64_t l = plane0[a2] + a1;
+        return (l < plane0[a2 + 1]) ? l : -1;
+    };
+    // columns of Q: (a_0, a_1) with t(a_0, a_1) > C, i.e. a_0 < len(line (a_1, C))
+    W.ncolq = 0;
+    for (int a1 = 0; a1 < kMaxRegT; ++a1) {
+        const int64_t l = line_of(a1, C);
+        W.cb[a1] = W.ncolq;
+        W.rq[a1] = (a1 < n1 && l >= 0) ? LEN(l) : 0;
+        W.ncolq += W.rq[a1];
+    }
+    const int TG = 384;
+    for (int p = 0; p < 2; ++p) {
+        const int64_t l_lo = p == 0 ? 0 : LP, l_hi = p == 0 ? LP : N1;
+        const int a2_lo = p == 0 ? 0 : C, a2_hi = p == 0 ? C : planes;
+        for (int h = 0; h < 3; ++h) {
+            std::vector<WholeItem> nat;
+            if (h == 0) {
+                for (int64_t l = l_lo; l < l_hi; ++l)
+                    nat.push_back({LEN(l), uint32_t(line_off[l] - W.e0[p]) | (uint32_t(LEN(l)) << 16)});
+            } else if (h == 1) {
+                for (int a2 = a2_lo; a2 < a2_hi; ++a2) {
+                    while (W.seo.size() % 4) W.seo.push_back(0);
+                    const uint32_t s0 = uint32_t(W.seo.size());
+                    const int64_t f0 = plane0[a2], nl = plane0[a2 + 1] - f0;
+                    for (int64_t r = 0; r < nl; ++r) W.seo.push_back(uint16_t(line_off[f0 + r] - W.e0[p]));
+                    for (int lane = 0; lane < LEN(f0); ++lane) {
+                        int t = 0;
+                        while (t < nl && LEN(f0 + t) > lane) ++t;
+                        nat.push_back({t, s0 | (uint32_t(t) << 16) | (uint32_t(lane) << 22) | (uint32_t(a2) << 27)});
+                    }
+                }
+            } else {
+                for (int a1 = 0; a1 < n1; ++a1) {
+                    if (line_of(a1, 0) < 0) break;
+                    while (W.seo.size() % 4) W.seo.push_back(0);
+                    const uint32_t s0 = uint32_t(W.seo.size());
+                    int nl = 0;  // lines (a_1, a_2) of the whole column group
+                    while (line_of(a1, nl) >= 0) ++nl;
+                    // part Q: C placeholders first, so that entry k of the list belongs to row k in both parts
+                    if (p == 1) for (int q = 0; q < C; ++q) W.seo.push_back(0);
+                    for (int a2 = a2_lo; a2 < std::min(a2_hi, nl); ++a2) W.seo.push_back(uint16_t(line_off[line_of(a1, a2)] - W.e0[p]));
+                    const int lanes = LEN(line_of(a1, 0));
+                    for (int lane = 0; lane < lanes; ++lane) {
+                        int t = 0;
+                        while (t < nl && LEN(line_of(a1, t)) > lane) ++t;
+                        if (p == 0) {
+                            const int tp = std::min(t, C);
+                            nat.push_back({tp, s0 | (uint32_t(tp) << 16) | (uint32_t(lane) << 22) | (uint32_t(a1) << 27)});
+                        } else if (t > C) {
+                            nat.push_back({t, s0 | (uint32_t(t) << 16) | (uint32_t(lane) << 22) | (uint32_t(a1) << 27)});
+                        }
+                    }
+                }
+            }
+            for (const WholeItem &it : nat) W.max_t = std::max(W.max_t, it.t);
+            W.item_off[p][h] = int32_t(W.items.size());
+            W.n_items[p][h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, 1, false, W.items);
+        }
+    }
+    for (int q = 0; q < kMaxRegT + 8 || W.seo.size() % 8; ++q) W.seo.push_back(0);
+    if (W.seo.size() > 65536) return;
     W.ok = true;
 }
 
@@ -493,6 +612,8 @@ bool table_view(const lpfnt_index *ix, int what, int h, const void **ptr, size_t
     if (what == LPFNT_TAB_LINE_ORDER) return set(x.line_order.data(), 4, x.line_order.size(), int64_t(x.line_order.size()));
     if (what == LPFNT_TAB_WHOLE_ITEMS) return set(x.whole.items.data(), 4, x.whole.items.size(), int64_t(x.whole.items.size()));
     if (what == LPFNT_TAB_WHOLE_SEO) return set(x.whole.seo.data(), 2, x.whole.seo.size(), int64_t(x.whole.seo.size()));
+    if (what == LPFNT_TAB_WSPLIT_ITEMS) return set(x.wsplit.items.data(), 4, x.wsplit.items.size(), int64_t(x.wsplit.items.size()));
+    if (what == LPFNT_TAB_WSPLIT_SEO) return set(x.wsplit.seo.data(), 2, x.wsplit.seo.size(), int64_t(x.wsplit.seo.size()));
     if (what == LPFNT_TAB_LINE_LAST) return set(x.line_last.data(), 1, x.line_last.size(), int64_t(x.line_last.size()));
     if (h < 1 || h >= x.m) return false;
     const DimTable &D = x.dims[h];
@@ -593,6 +714,23 @@ int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order, int fibr
     if (fibres < 1 || fibres > 3) { set_error("whole_build: fibres must be 1, 2 (two per thread, side by side) or 3 (two per thread, one after the other)"); return LPFNT_EINVAL; }
     index->hx.build_whole(threads, order < 0 ? kWholeDefaultOrder : order, fibres);
     return LPFNT_OK;
+}
+int lpfnt_index_wsplit_build(lpfnt_index *index, int C, int order) {
+    if (!index) { set_error("index is null"); return LPFNT_EINVAL; }
+    index->hx.build_whole_split(C, order < 0 ? kWholeDefaultOrder : order);
+    return LPFNT_OK;
+}
+int lpfnt_index_wsplit_meta(const lpfnt_index *index, int32_t *meta) {
+    if (!index || !meta) { set_error("wsplit_meta: bad arguments"); return LPFNT_EINVAL; }
+    const WholeSplitHost &W = index->hx.wsplit;
+    int q = 0;
+    meta[q++] = W.ok ? 1 : 0; meta[q++] = W.C;
+    for (int p = 0; p < 2; ++p) { meta[q++] = W.e0[p]; meta[q++] = W.ne[p]; }
+    for (int p = 0; p < 2; ++p) for (int h = 0; h < 3; ++h) { meta[q++] = W.item_off[p][h]; meta[q++] = W.n_items[p][h]; }
+    meta[q++] = W.ncolq;
+    for (int a = 0; a < kMaxRegT; ++a) meta[q++] = W.cb[a];
+    for (int a = 0; a < kMaxRegT; ++a) meta[q++] = W.rq[a];
+    return q;  // 83 entries
 }
 int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta) {
     if (!index || !meta) { set_error("whole_meta: bad arguments"); return LPFNT_EINVAL; }

@@ -65,6 +65,18 @@ struct WholeHost {
     std::vector<uint16_t> seo;
 };
 
+// Tables of the split whole-function kernel (see HostIndex::build_whole_split).
+struct WholeSplitHost {
+    bool ok = false;
+    int C = 0;                              // planes a_2 < C form part P, the others part Q
+    int32_t e0[2] = {0, 0}, ne[2] = {0, 0}; // element range of the parts
+    int32_t item_off[2][3] = {{0, 0, 0}, {0, 0, 0}}, n_items[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int32_t cb[kMaxRegT] = {0}, rq[kMaxRegT] = {0};  // columns of Q: cb[a_1] + a_0 for a_0 < rq[a_1]
+    int32_t ncolq = 0, max_t = 0;
+    std::vector<uint32_t> items;
+    std::vector<uint16_t> seo;
+};
+
 // Host-side index structure derived from the multi-index array A (colex order).
 struct HostIndex {
     int m = 0, n = 0;
@@ -75,6 +87,7 @@ struct HostIndex {
     std::vector<DimTable> dims;          // index h = 0..m-1 (entry 0 unused)
     std::vector<uint8_t> line_last;      // N_1: a_{m-1} of every line (m >= 2, n <= 255)
     WholeHost whole;
+    WholeSplitHost wsplit;
     std::vector<int32_t> line_order;     // N_1: lines ordered by length inside every chunk of kLineChunk
     std::vector<SortedItem> eval_line;   // N_1: {padded coefficient offset, line length}
     std::vector<EvalBlock> eval_block;   // blocks of lines staged together by the eval kernel
@@ -86,6 +99,8 @@ struct HostIndex {
     // 1 / 2 length classes of 8 / 16 (natural order inside a class), 3 natural; bit 6: chunks dealt to the warps by the
     // pipe-sharing model instead of the snake order
     void build_whole(int threads, int order, int fibres);
+    // (re)build `wsplit` (m = 3): C = split plane (<= 0: the one that balances the parts)
+    void build_whole_split(int C, int order);
 };
 constexpr int kWholeDefaultOrder = 0 | (2 << 2) | (2 << 4) | 64;
 

@@ -81,6 +81,30 @@ cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibre
 }
 
 template <>
+cudaError_t launch_whole_split<T>(bool fma, bool timeline, const WholeSplitArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s) {
+#if LPFNT_MAXT >= 24
+    PackedTri<T> M;
+    std::memcpy(M.v, tri, sizeof(M.v));
+    auto go = [&](auto kern) -> cudaError_t {
+        if (set_attr) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kSplitThreads, smem, s>>>(a, M);
+        return cudaGetLastError();
+    };
+#if LPFNT_MAXT == 32
+    if (timeline) return fma ? go(k_whole_split<T, true, true>) : go(k_whole_split<T, false, true>);
+#endif
+    (void)timeline;
+    return fma ? go(k_whole_split<T, true>) : go(k_whole_split<T, false>);
+#else
+    (void)fma; (void)timeline; (void)a; (void)tri; (void)grid; (void)smem; (void)set_attr; (void)s;
+    return cudaErrorInvalidValue;
+#endif
+}
+
+template <>
 cudaError_t launch_slab<T>(int mode, bool fma, const SlabArgs &a, const double *tri, int grid, cudaStream_t s) {
     PackedTri<T> M;
     std::memcpy(M.v, tri, sizeof(M.v));

@@ -5,6 +5,7 @@
 
 #include "sweep_kernels.cuh"
 #include "whole_kernel.cuh"
+#include "whole_split_kernel.cuh"
 
 namespace lpfnt {
 
@@ -23,6 +24,10 @@ cudaError_t launch_slab(int mode, bool fma, const SlabArgs &a, const double *tri
 // set_attr: opt in to `smem` bytes of dynamic shared memory first (per device and kernel, tracked by the plan).
 template <int MAXT>
 cudaError_t launch_whole(int mode, bool fma, int threads, int rows, int fibres, bool timeline, const WholeArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s);
+
+// split whole-function kernel (m = 3, lower mat-vec, capacities 24 and 32): two units per function, two CTAs per SM
+template <int MAXT>
+cudaError_t launch_whole_split(bool fma, bool timeline, const WholeSplitArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s);
 
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
 cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int batch, bool restrict_, cudaStream_t s);

@@ -103,3 +103,67 @@ def whole_function(x, tabs: nat.IndexTables, M, n1, mode="lower"):
         Y = apply_tri(X, M, mode)
         buf[idx[valid]] = Y[valid]
     return buf
+
+
+def whole_function_split(x, tabs: nat.IndexTables, M, n1):
+    """Emulates k_whole_split (lower mat-vec, m = 3) from its REAL tables: unit P (planes a_2 < C) sweeps coordinates 0, 1
+    in place, exports the coordinate-1 results of the columns that reach beyond C to the scratch [a_2][column], folds the rows
+    k < C of the last coordinate; unit Q sweeps its planes, then folds the rows k >= C from the first term on (j < C from the
+    scratch, j >= C from its buffer)."""
+    meta = tabs.wsplit_meta()
+    assert meta["ok"], "set is not eligible for the split whole-function kernel"
+    items = tabs.table(nat.TAB_WSPLIT_ITEMS).astype(np.int64)
+    seo = tabs.table(nat.TAB_WSPLIT_SEO).astype(np.int64)
+    C, ncolq, cb, rq = meta["C"], meta["ncolq"], np.array(meta["cb"]), np.array(meta["rq"])
+    out = np.full_like(x, np.nan)
+    scratch = np.full((C, max(ncolq, 1)), np.nan)
+    kk = np.arange(n1)[None, :]
+    seen = np.zeros(len(x), dtype=int)
+    for p in range(2):
+        e0, ne = meta["e0"][p], meta["ne"][p]
+        buf = x[e0:e0 + ne].copy()
+        for h in range(3):
+            lst = items[meta["item_off"][p][h]: meta["item_off"][p][h] + meta["n_items"][p][h]]
+            t = (lst >> 16) & 63
+            live = t > 0
+            lst, t = lst[live], t[live]
+            lo, lane, aux = lst & 0xFFFF, (lst >> 22) & 31, (lst >> 27) & 31
+            if h == 0:
+                valid = kk < t[:, None]
+                idx = lo[:, None] + kk
+                X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
+                Y = apply_tri(X, M, "lower")
+                assert len(np.unique(idx[valid])) == ne
+                buf[idx[valid]] = Y[valid]
+            elif h == 1:
+                valid = kk < t[:, None]
+                idx = seo[np.where(valid, lo[:, None] + kk, 0)] + lane[:, None]
+                X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
+                Y = apply_tri(X, M, "lower")
+                assert len(np.unique(idx[valid])) == ne
+                buf[idx[valid]] = Y[valid]
+                if p == 0:  # export: element k of the fibre is (a_0 = lane, a_1 = k, a_2 = aux)
+                    exp = valid & (lane[:, None] < rq[np.minimum(kk, 31)])
+                    rows, cols = np.nonzero(exp)
+                    scratch[aux[rows], cb[cols] + lane[rows]] = Y[rows, cols]
+            elif p == 0:  # rows k < C of every column
+                valid = kk < t[:, None]
+                idx = seo[np.where(valid, lo[:, None] + kk, 0)] + lane[:, None]
+                X = np.where(valid, buf[np.where(valid, idx, 0)], 0.0)
+                Y = apply_tri(X, M, "lower")
+                out[e0 + idx[valid]] = Y[valid]
+                np.add.at(seen, e0 + idx[valid], 1)
+            else:  # rows k >= C: x[j < C] from the scratch, x[j >= C] from the buffer (seo lists start at plane C)
+                assert np.all(t > C)
+                col = cb[aux] + lane
+                assert np.all(lane < rq[aux])
+                valid_hi = (kk >= C) & (kk < t[:, None])
+                idx = seo[np.where(valid_hi, lo[:, None] + kk, 0)] + lane[:, None]  # the lists of part Q start with C placeholders
+                X = np.where(valid_hi, buf[np.where(valid_hi, idx, 0)], 0.0)
+                X[:, :C] = scratch[:, col].T
+                assert not np.isnan(X[:, :C]).any(), "scratch entry missing"
+                Y = apply_tri(X, M, "lower")
+                out[e0 + idx[valid_hi]] = Y[valid_hi]
+                np.add.at(seen, e0 + idx[valid_hi], 1)
+    assert np.all(seen == 1), "outputs are not covered exactly once"
+    return out

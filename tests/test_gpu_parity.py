@@ -414,6 +414,9 @@ def test_eval_few_points_split_path(T, m, n, p, P):
     {"use_whole": 1, "whole_threads": 384, "whole_fibres": 2},
     {"use_whole": 1, "whole_threads": 384, "whole_fibres": 2, "whole_order": 0},
     {"use_whole": 1, "whole_threads_exact": 384, "whole_fibres_exact": 2, "whole_threads_fma": 768, "whole_fibres_fma": 1},
+    {"use_whole": 1, "whole_split": 1},
+    {"use_whole": 1, "whole_split": 1, "whole_split_c": 7},
+    {"use_whole": 1, "whole_split": 1, "whole_split_order": 64},
     {"use_whole": 1, "whole_fibres": 3},
     {"use_whole": 1, "whole_fibres": 3, "whole_order": 0},
     {"use_whole": 1, "whole_threads": 768, "whole_fibres": 1},

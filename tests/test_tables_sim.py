@@ -105,3 +105,30 @@ def test_emulated_whole_function_kernel_matches_reference(name, threads, fibres,
         z[P] = y
         y = z
     assert np.array_equal(y, g["ifnt"][0])
+
+
+@pytest.mark.parametrize("C", [0, 5, 13])
+@pytest.mark.parametrize("name", ["c4_d3n30", "c2_d3n20_leja", "d3n12_p1"])
+def test_emulated_split_whole_function_kernel_matches_reference(name, C, built_lib):
+    """k_whole_split (two units per function, so that two CTAs fit on an SM) from its real tables -- bit-exact, including the
+    hand-over of the coordinate-1 results of part P to the last sweep of part Q."""
+    g = load_case(name)
+    n = int(g["n"])
+    n1 = n + 1
+    tabs = nat.IndexTables(g["A"].astype(np.int64), n)
+    tabs.wsplit_build(C=min(C, n))
+    meta = tabs.wsplit_meta()
+    assert meta["ok"] and sum(meta["ne"]) == len(g["A"])
+    P = g["P"] if bool(g["colex"]) else None
+    v = g["values"][0]
+    x = v[P] if P is not None else v.copy()
+    assert bool(g["precomputation"])
+    M = U.unpack_lower(g["inv_Vx_lt"], n1)
+    assert np.array_equal(sim.whole_function_split(x, tabs, M, n1), g["fnt"][0])
+    V = U.unpack_lower(g["Vx_lt"], n1)
+    y = sim.whole_function_split(g["fnt"][0], tabs, V, n1)
+    if P is not None:
+        z = np.empty_like(y)
+        z[P] = y
+        y = z
+    assert np.array_equal(y, g["ifnt"][0])
