@@ -371,7 +371,12 @@ class Transform:
         return lpset.ordinal_embedding(self._A, t.multi_index_set)
 
     def _transfer(self, coefficients, t: "Transform", restrict: bool):
-        phi = np.ascontiguousarray(self.embed(t), dtype=np.int64)
+        # the index map only depends on the two spaces: computed once per partner (keyed by its defining parameters)
+        cache = self.__dict__.setdefault("_phi_cache", {})
+        key = (t._m, t._n, t._p, len(t), t._x.tobytes())
+        phi = cache.get(key)
+        if phi is None:
+            phi = cache[key] = np.ascontiguousarray(self.embed(t), dtype=np.int64)
         src = t if restrict else self
         x, dev, sq = src._vec_in(coefficients, "restrict" if restrict else "prolong")
         n_out = self._N_0 if restrict else len(t)

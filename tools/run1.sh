@@ -1,3 +1,5 @@
 set -x
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 0 --opt whole_split=1 --sweep whole_split_skew=0,5000,10000,20000,30000,45000
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 1 --opt whole_split=1 --sweep whole_split_skew=0,10000,20000,30000
+python -m pytest tests -m gpu -x -q -k "alternative or odd or golden or whole" 2>&1 | tail -3
+python tools/quick.py --batch 4096 --iters 10 --trace 0
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --sweep whole_order_exact=104,64,100,96,68,80
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --sweep whole_order_fma=104,64,100,96,68,80
