@@ -510,6 +510,7 @@ void free_wsplit(lpfnt_plan *p) {
 int upload_wsplit(lpfnt_plan *p) {
     lpfnt_plan::WholeSplit &W = p->wsplit;
     free_wsplit(p);
+    for (int k = 400; k < 408; ++k) p->whole_attr_set[k] = false;  // the shared-memory size changes with the tables
     if (!p->hx || p->m != 3) return LPFNT_OK;
     // the split plane: as given, else the one for which the larger part is smallest among those that fit twice into an SM
     int best_c = 0;

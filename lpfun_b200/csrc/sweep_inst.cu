@@ -1,4 +1,6 @@
 // Instantiates the register-fibre sweep kernels for one fibre capacity LPFNT_MAXT.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sweep_launch.h"
@@ -89,6 +91,14 @@ cudaError_t launch_whole_split<T>(bool fma, bool timeline, const WholeSplitArgs 
         if (set_attr) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
+            // two CTAs per SM need the full shared-memory carve-out
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            if (std::getenv("LPFNT_DEBUG_OCCUPANCY")) {
+                int nb = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kSplitThreads, smem);
+                std::fprintf(stderr, "k_whole_split: %zu bytes of dynamic shared memory, %d CTA(s) per SM\n", smem, nb);
+            }
         }
         kern<<<grid, kSplitThreads, smem, s>>>(a, M);
         return cudaGetLastError();

@@ -1,5 +1,4 @@
-set -x
-python -m pytest tests -m gpu -x -q -k "alternative or odd or golden or whole" 2>&1 | tail -3
-python tools/quick.py --batch 4096 --iters 10 --trace 0
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --sweep whole_order_exact=104,64,100,96,68,80
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --sweep whole_order_fma=104,64,100,96,68,80
+export LPFNT_DEBUG_OCCUPANCY=1
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 0 --opt whole_split=1 2>&1 | tail -4
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 1 --opt whole_split=1 2>&1 | tail -4
+python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 0 --opt whole_split=1 --sweep whole_split_c=11,12,13 2>&1 | tail -8
