@@ -128,6 +128,7 @@ struct lpfnt_plan {
         int2 *d_item0 = nullptr, *d_item1 = nullptr;
     } slabs;
     int use_slab = 1;
+    int slab_ctas = 4;                       // CTAs per SM the persistent slab grid is sized for (capacities <= 24)
     int use_cta_cap = 1;                     // k_sweep_groups: per-CTA row capacity (8 / 16 / MAXT)
     int64_t host_chunk_bytes = 0;            // host-pointer calls: bytes per pipelined chunk (H2D | sweeps | D2H on two lanes); 0 = automatic
     long long *d_timeline = nullptr;         // development: clock64 stamps of k_whole (option "timeline")
@@ -388,7 +389,7 @@ int launch_slab_pass(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
         const int nb = int(std::min<int64_t>(int64_t(1) << 24, batch - b0));
         a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
         const int64_t units = int64_t(a.n_slabs) * nb;
-        const int grid = int(std::min<int64_t>(units, int64_t(p->num_sms) * 3));
+        const int grid = int(std::min<int64_t>(units, int64_t(p->num_sms) * (cap <= 24 ? p->slab_ctas : 3)));
         cudaError_t e = cudaSuccess;
         trace_begin(p, 1601, s);
         LAUNCH_CAP(cap, launch_slab<8>(mode, spec.fma, a, tri, grid, s), launch_slab<16>(mode, spec.fma, a, tri, grid, s),
@@ -1004,6 +1005,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
         } else if (!value && p->d_timeline) { CK(cudaDeviceSynchronize()); cudaFree(p->d_timeline); p->d_timeline = nullptr; }
         return LPFNT_OK;
     }
+    if (std::strcmp(name, "slab_ctas") == 0) { p->slab_ctas = int(std::max<int64_t>(1, std::min<int64_t>(value, 4))); return LPFNT_OK; }
     if (std::strcmp(name, "use_slab") == 0) {
         p->use_slab = value ? 1 : 0;
         if (value == 2 && p->slabs.n_slabs > 0) p->slabs.ok = true;  // 2: force the slab kernel even for sparsely filled slabs (tests)

@@ -355,7 +355,7 @@ struct SlabArgs {
 };
 
 template <int MAXT, int MODE, bool FMA>
-__global__ void __launch_bounds__(kSlabThreads, 3) k_slab(const SlabArgs a, const __grid_constant__ PackedTri<MAXT> M) {
+__global__ void __launch_bounds__(kSlabThreads, MAXT <= 24 ? 4 : 3) k_slab(const SlabArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     __shared__ __align__(16) double buf[kSlabElems];
     __shared__ int2 sitem0[kSlabThreads], sitem1[kSlabThreads];
     __shared__ uint16_t seo[32 + kSlabThreads];

@@ -1,4 +1,3 @@
-export LPFNT_DEBUG_OCCUPANCY=1
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 0 --opt whole_split=1 2>&1 | tail -4
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 1 --opt whole_split=1 2>&1 | tail -4
-python tools/quick.py --batch 4096 --iters 10 --trace 0 --check 0 --colex 0 --opt whole_split=1 --sweep whole_split_c=11,12,13 2>&1 | tail -8
+for o in 4 3; do python tools/quick.py --m 6 --n 20 --batch 1 --iters 20 --flush --check 0 --opt slab_ctas=$o 2>&1 | grep -E "ms/step|1601"; done
+for o in 4 3; do python tools/quick.py --m 4 --n 20 --batch 64 --iters 20 --check 0 --opt slab_ctas=$o 2>&1 | grep -E "ms/step|1601"; done
+python -m pytest tests -m gpu -x -q -k "golden or c3 or alternative" 2>&1 | tail -2
