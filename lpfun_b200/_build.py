@@ -18,7 +18,8 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "liblpfnt.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xfatbin=-compress-all", "-Xcompiler", "-fPIC"]
+GROUP_LANES = os.environ.get("LPFNT_GROUP_LANES")
+COMMON = ([f"-DLPFNT_GROUP_LANES={GROUP_LANES}"] if GROUP_LANES else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xfatbin=-compress-all", "-Xcompiler", "-fPIC"]
 
 # (source, object name, extra defines)
 UNITS = [

@@ -274,9 +274,10 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         std::stable_sort(D.groups.begin(), D.groups.end(), [](const SortedItem &a, const SortedItem &b) {
             return (((a.y >> 8) & 0xff) + kGroupClass - 1) / kGroupClass > (((b.y >> 8) & 0xff) + kGroupClass - 1) / kGroupClass;
         });
-        D.group_cta_cap.assign((D.groups.size() + 15) / 16, 0);
+        constexpr size_t kRunsPerCta = 128 / kGroupLanes;  // one CTA of k_sweep_groups = 128 threads
+        D.group_cta_cap.assign((D.groups.size() + kRunsPerCta - 1) / kRunsPerCta, 0);
         for (size_t g = 0; g < D.groups.size(); ++g)
-            D.group_cta_cap[g / 16] = std::max<uint8_t>(D.group_cta_cap[g / 16], uint8_t((D.groups[g].y >> 8) & 0xff));
+            D.group_cta_cap[g / kRunsPerCta] = std::max<uint8_t>(D.group_cta_cap[g / kRunsPerCta], uint8_t((D.groups[g].y >> 8) & 0xff));
         // height of every lane of every group (8 bytes per group, 0 for absent lanes)
         D.group_t.assign(D.groups.size() * kGroupLanes, 0);
         for (size_t g = 0; g < D.groups.size(); ++g) {

@@ -12,7 +12,10 @@ constexpr int kMaxDim = 12;     // spatial dimensions supported by the fast kern
 constexpr int kMaxRegT = 32;    // longest fibre held in registers by the unrolled kernels (n+1 <= 32)
 constexpr int kEvalBlockLines = 256;  // lines per shared-memory block of the eval kernel
 constexpr int kEvalBlockElems = 2048;  // padded doubles per block (16 KB)
-constexpr int kGroupLanes = 8;   // consecutive lanes of a fibre that stay together in k_sweep_groups
+#ifndef LPFNT_GROUP_LANES
+#define LPFNT_GROUP_LANES 8
+#endif
+constexpr int kGroupLanes = LPFNT_GROUP_LANES;   // consecutive lanes of a fibre that stay together in k_sweep_groups
 constexpr int kLineChunk = 128;  // lines per CTA of k_sweep_lines
 constexpr int kGroupClass = 4;  // lane groups of k_sweep_groups are ordered by height class of this many rows
 constexpr int kWholeSmemLimit = 227 * 1024;   // one CTA per SM

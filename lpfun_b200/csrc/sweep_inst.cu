@@ -23,7 +23,7 @@ cudaError_t line_launch(const LineSweepArgs &a, const PackedTri<T> &M, int batch
 
 template <int MODE, bool FMA>
 cudaError_t group_launch(const GroupSweepArgs &a, const PackedTri<T> &M, int batch, cudaStream_t s) {
-    dim3 grid((8 * int64_t(a.num_groups) + kSweepThreads - 1) / kSweepThreads, batch);
+    dim3 grid((kRunLanes * int64_t(a.num_groups) + kSweepThreads - 1) / kSweepThreads, batch);
     k_sweep_groups<T, MODE, FMA, kSweepThreads><<<grid, kSweepThreads, 0, s>>>(a, M);
     return cudaGetLastError();
 }

@@ -18,6 +18,11 @@
 
 namespace lpfnt {
 
+#ifndef LPFNT_GROUP_LANES
+#define LPFNT_GROUP_LANES 8
+#endif
+constexpr int kRunLanes = LPFNT_GROUP_LANES;  // consecutive lanes of a fibre that stay together in k_sweep_groups (host: kGroupLanes)
+
 enum SweepMode : int {
     kLowerMatvec = 0,  // out_k = sum_{j<=k} L[k,j] x_j                (fnt with inv V, ifnt, dxT)
     kUpperMatvec = 1,  // out_k = sum_{j>=k} U[k,j] x_j                (dx)
@@ -263,15 +268,15 @@ __device__ __forceinline__ void sweep_group_body(const GroupSweepArgs &a, const 
     // and handed around the 8 threads of the run with shuffles: one global latency ahead of the
     // data loads instead of a dependent descriptor load per row, and nothing to re-load for the stores
     // (ncu: descriptor look-ups and their dependent compares were 2/3 of the issued instructions).
-    constexpr int NR = CAP / 8;
+    constexpr int GL = kRunLanes, NR = (CAP + GL - 1) / GL;
     int offs[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) offs[i] = (sub + 8 * i < nl) ? __ldg(a.ent + p0 + sub + 8 * i).x : 0;
-    const int src_base = (threadIdx.x & 31) & ~7;
+    for (int i = 0; i < NR; ++i) offs[i] = (sub + GL * i < nl) ? __ldg(a.ent + p0 + sub + GL * i).x : 0;
+    const int src_base = (threadIdx.x & 31) & ~(GL - 1);
     double x[CAP];
 #pragma unroll
     for (int k = 0; k < CAP; ++k) {
-        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
+        const int off = __shfl_sync(0xffffffffu, offs[k / GL], src_base + (k % GL));
         x[k] = (k < t) ? in[off + lane] : 0.0;
     }
     apply_fibre<CAP, MODE, FMA>(x, t, M, __reduce_max_sync(0xffffffffu, t));
@@ -280,7 +285,7 @@ __device__ __forceinline__ void sweep_group_body(const GroupSweepArgs &a, const 
     const int t2 = live ? int(*reinterpret_cast<const volatile uint8_t *>(a.group_t + j)) : 0;
 #pragma unroll
     for (int k = 0; k < CAP; ++k) {
-        const int off = __shfl_sync(0xffffffffu, offs[k >> 3], src_base + (k & 7));
+        const int off = __shfl_sync(0xffffffffu, offs[k / GL], src_base + (k % GL));
         if (k < t2) {
             const int e = off + lane;
             out[a.perm_out ? a.perm_out[e] : e] = x[k];
@@ -296,7 +301,7 @@ __device__ __forceinline__ void sweep_group_body(const GroupSweepArgs &a, const 
 template <int MAXT, int MODE, bool FMA, int THREADS>
 __global__ void __launch_bounds__(THREADS, MAXT <= 24 ? 8 : 6) k_sweep_groups(const GroupSweepArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     const int j = blockIdx.x * THREADS + threadIdx.x;
-    const int g = j >> 3, sub = j & 7;
+    const int g = j / kRunLanes, sub = j % kRunLanes;
     const bool live = g < a.num_groups;  // whole warps stay alive for the shuffles below
     const int2 gr = live ? __ldg(a.groups + g) : make_int2(0, 0);
     const int p0 = gr.x, lane = (gr.y & 0xff) + sub, nl = (gr.y >> 8) & 0xff;
