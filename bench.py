@@ -435,14 +435,95 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
         i2 = np.arange(a2, a2 + Bc)
         want = torch.as_tensor(base[i2 % 64] * (1.0 + 0.001 * (i2 // 64))[:, None], device=dev)
         ok = bool((full[0][nxt * Bc:(nxt + 1) * Bc] - want).abs().max().item() < 1e-9)
-    return {"workload": f"Transform(3,30), {Btot} functions in total, {Bl} per rank, fnt+ifnt, reconstructions all-gathered to every rank "
-                        f"({chunks} chunks, gather of chunk k on a side stream behind the sweeps of chunk k+1)",
-            "scaling": "strong", "functions_total": Btot, "ms_per_step": ms, "GDOF_s": 2.0 * N * Btot / (ms * 1e-3) / 1e9,
-            "ms_sweeps_only": ms_sweeps, "ms_gather_only": ms_gather,
-            "gather_exposed_share": max(0.0, (ms - ms_sweeps) / ms) if ms > 0 else 0.0,
+    # the same step with OUR OWN gather over NVLink peer memory (lpfun_b200.sharding.PushGather, a symmetric buffer):
+    #   copy_engine: chunk k goes to the other ranks' copies by the copy engines (cudaMemcpyAsync to the peer mappings) on a side
+    #             stream while chunk k+1 is swept -- no SM is taken from the persistent sweep kernels;
+    #   copy_*  : the same with a streaming copy kernel (lpfnt_push_rows): 16-byte stores per peer mapping, or ONE multimem.st.v4
+    #             through the NVSwitch multicast (the sweep kernels fill the SMs, so this one only runs between them);
+    #   fused_* : k_whole itself stores every reconstruction into the same offset of every rank's copy (lpfnt_plan_set_push).
+    # The ranks only synchronise afterwards (signal-pad barrier).
+    push = None
+    if world > 1:
+        from lpfun_b200.sharding import PushGather
+
+        push = {}
+        for mode in ("copy_engine", "copy_peer_stores", "copy_multicast", "fused_peer_stores", "fused_multicast"):
+            use_mc, fused = mode.endswith("multicast"), mode.startswith("fused")
+            try:
+                pg = PushGather(t, Btot, use_multicast=use_mc, fused=fused)
+                if use_mc and not pg.multicast:
+                    pg.close()
+                    continue
+                mine = pg.local_rows()
+                # chunks in whole rounds of the persistent sweep kernel (multiples of the SM count), the last one short: its
+                # transfer is the only one that nothing hides
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                rounds = -(-Bl // sms)
+                r_last = max(1, rounds // 5)
+                r_rest = rounds - r_last
+                cuts = [0]
+                for q in range(2):
+                    if r_rest > 0:
+                        take = (r_rest + (1 - q)) // 2 if q == 0 else r_rest - (r_rest + 1) // 2
+                        if take > 0:
+                            cuts.append(min(Bl, cuts[-1] + take * sms))
+                if cuts[-1] < Bl:
+                    cuts.append(Bl)
+                bounds = list(zip(cuts[:-1], cuts[1:]))
+
+                def step_push():
+                    if fused:  # the last sweep's stores go to every rank
+                        t.fnt(vals, out=coef); t.ifnt(coef, out=mine)
+                    else:      # chunk k is copied to the peers on the side stream while chunk k+1 is swept
+                        for lo, hi in bounds:
+                            sl = slice(lo, hi)
+                            t.fnt(vals[sl], out=coef[sl]); t.ifnt(coef[sl], out=mine[sl])
+                            comm.wait_stream(torch.cuda.current_stream(dev))
+                            pg.push_rows(lo, hi, stream=comm, engine="ce" if mode == "copy_engine" else "sm")
+                        torch.cuda.current_stream(dev).wait_stream(comm)
+                    pg.barrier()
+
+                for _ in range(2):
+                    step_push()
+                torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(K):
+                    step_push()
+                e1.record(); torch.cuda.synchronize()
+                tt = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                nxt = (rank + 1) % world
+                a2, b2 = row_block(Btot, nxt, world)
+                i2 = np.arange(a2, min(b2, a2 + 64))
+                want = torch.as_tensor(base[i2 % 64] * (1.0 + 0.001 * (i2 // 64))[:, None], device=dev)
+                good = bool((pg.full[a2:a2 + len(i2)] - want).abs().max().item() < 1e-9)
+                push[mode] = {"ms_per_step": float(tt.item()), "GDOF_s": 2.0 * N * Btot / (float(tt.item()) * 1e-3) / 1e9, "gather_checked": good}
+                if not fused:
+                    push[mode]["chunks"] = [hi - lo for lo, hi in bounds]
+                pg.close()
+                del pg, mine
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001
+                push[mode] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    nccl = {"ms_per_step": ms, "GDOF_s": 2.0 * N * Btot / (ms * 1e-3) / 1e9, "ms_gather_only": ms_gather,
+            "gather_exposed_share": max(0.0, (ms - ms_sweeps) / ms) if ms > 0 else 0.0, "chunks": chunks,
+            "collective": "ncclAllGather (torch.distributed all_gather_into_tensor) on a side stream", "gather_checked": ok}
+    best_ms, how = ms, ("ncclAllGather on a side stream" if world > 1 else "none (one rank)")
+    if push:
+        names = {"copy_engine": "own gather: copy engines store chunk k into the peers' mappings of a symmetric buffer (NVLink) behind the sweeps of chunk k+1",
+                 "copy_peer_stores": "own gather: streaming copy kernel, 16-byte stores into the peers' mappings (NVLink)",
+                 "copy_multicast": "own gather: streaming copy kernel, multimem.st.v4 through the NVSwitch multicast mapping",
+                 "fused_peer_stores": "own gather fused into k_whole: the last sweep stores into every peer's mapping",
+                 "fused_multicast": "own gather fused into k_whole: multimem.st through the NVSwitch multicast mapping"}
+        for k, v in push.items():
+            if "ms_per_step" in v and v.get("gather_checked") and v["ms_per_step"] < best_ms:
+                best_ms, how = v["ms_per_step"], names[k]
+    return {"workload": f"Transform(3,30), {Btot} functions in total, {Bl} per rank, fnt+ifnt, reconstructions gathered to every rank",
+            "scaling": "strong", "functions_total": Btot, "ms_per_step": best_ms, "GDOF_s": 2.0 * N * Btot / (best_ms * 1e-3) / 1e9,
+            "gather": how, "ms_sweeps_only": ms_sweeps, "gather_exposed_share": max(0.0, (best_ms - ms_sweeps) / best_ms) if best_ms > 0 else 0.0,
             "gathered_bytes_per_rank": int((world - 1) * Bl * N * 8) if world > 1 else 0,
-            "collective": "ncclAllGather (torch.distributed all_gather_into_tensor)" if world > 1 else "none (one rank)",
-            "comm_nranks_seen": world, "gather_checked": ok}
+            "nccl": nccl if world > 1 else None, "own_gather": push, "comm_nranks_seen": world}
 
 
 def run_c5_sharded(args, torch, dist, lpfun_b200, dev, local, rank, world, K):

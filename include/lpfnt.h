@@ -150,6 +150,21 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
  * with L (:596-624).  chebyshev_eval != 0 makes eval use the T_k recurrence (chebyshev2point, utils.py:165). */
 int lpfnt_plan_set_upper_factors(lpfnt_plan *plan, const double *Vx_ut, const double *inv_Vx_ut, int chebyshev_eval);
 int lpfnt_plan_destroy(lpfnt_plan *plan);
+/* Fused all-gather (multi-GPU, one process per GPU): `local_base` .. + bytes is THIS rank's mapping of a symmetric buffer whose
+ * peer mappings (the own one included, n_peers <= 8) and NVSwitch multicast mapping (or NULL) are given.  A batched device-pointer
+ * fnt / ifnt whose `out` lies inside the region and that runs on the whole-function kernel then stores every result element into
+ * the same offset of EVERY rank's buffer: one multimem.st through the multicast mapping, else one store per peer mapping over
+ * NVLink -- the gather of the row blocks is done by the last sweep's stores, no collective follows (the ranks only synchronise).
+ * n_peers = 0 clears the region.  The reference has no distributed code; this serves BASELINE config 4 (batch sharded by rows). */
+/* The same gather as a streaming copy kernel: `bytes` at `src` (this rank's rows, already in its own copy of the symmetric buffer)
+ * are stored into the same place of every other rank's copy -- dst[r] are the peer mappings of `src` (the own one is skipped), or
+ * mc_dst its multicast mapping (one multimem.st.v4 per 16 bytes reaches every GPU).  Runs on `stream`, so it overlaps the sweeps of
+ * the next chunk on another stream. */
+int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, void *stream);
+/* ... and by the copy engines (one cudaMemcpyAsync per peer mapping): no SM is taken from the persistent sweep kernels, so the
+ * transfer really runs behind them */
+int lpfnt_push_rows_ce(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *stream);
+int lpfnt_plan_set_push(lpfnt_plan *plan, const void *local_base, int64_t bytes, int n_peers, const void *const *peer_bases, const void *mc_base);
 /* bytes of device memory held by the plan (tables + workspaces) */
 int64_t lpfnt_plan_device_bytes(const lpfnt_plan *plan);
 /* number of kernel launches enqueued by this plan since creation */

@@ -51,6 +51,9 @@ def _declare(L):
     L.lpfnt_sweep.argtypes = [vp, vp, i32, i32, i32, C.c_uint32, vp, vp, i64, i32, vp]
     L.lpfnt_embed_apply.argtypes = [i32, vp, i64, i64, vp, vp, i64, i32, i32, vp]
     L.lpfnt_plan_destroy.argtypes = [vp]
+    L.lpfnt_plan_set_push.argtypes = [vp, vp, i64, i32, C.POINTER(vp), vp]
+    L.lpfnt_push_rows.argtypes = [i32, vp, i64, i32, C.POINTER(vp), vp, vp]
+    L.lpfnt_push_rows_ce.argtypes = [i32, vp, i64, i32, C.POINTER(vp), vp]
     L.lpfnt_plan_device_bytes.restype = i64
     L.lpfnt_plan_device_bytes.argtypes = [vp]
     L.lpfnt_plan_launch_count.restype = i64

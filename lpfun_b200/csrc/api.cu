@@ -106,6 +106,8 @@ struct lpfnt_plan {
     } whole[2];
     struct WholeCfg { int threads = -1, fibres = -1, order = kWholeDefaultOrder, rows = -1; } wcfg[2];
     uint16_t *d_perm16 = nullptr;
+    // push region: every rank's mapping of a symmetric output buffer (lpfnt_plan_set_push)
+    struct Push { const char *local = nullptr; int64_t bytes = 0; int n = 0; char *peer[8] = {nullptr}; char *mc = nullptr; } push;
     // split whole-function kernel (two units per function, two CTAs per SM; m = 3, lower mat-vec)
     struct WholeSplit {
         WholeSplitHost h;                    // host copy (items / seo dropped after the upload)
@@ -117,7 +119,7 @@ struct lpfnt_plan {
     } wsplit;
     int use_whole_split = 0;                 // 0 off (default: measured slower), 1 whenever the tables exist, -1 automatic
     int whole_split_c = 0, whole_split_order = kWholeDefaultOrder, whole_split_skew = 0;
-    std::bitset<512> whole_attr_set;         // per kernel instantiation: dynamic shared memory opted in on this device
+    std::bitset<1024> whole_attr_set;         // per kernel instantiation: dynamic shared memory opted in on this device
     int use_whole = -1;                      // -1 auto (batches of >= 8 functions), 0 off, 1 always
     HostIndex *hx = nullptr;                 // kept for plans that can run the whole-function kernel (re-build of its tables)
     // slab kernel (coordinates 0 and 1 in one pass, any m >= 2; see k_slab)
@@ -473,16 +475,25 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     a.gather = gather ? 1 : 0; a.scatter = scatter ? 1 : 0;
     a.n_elem = int32_t(p->N); a.m = p->m;
     a.dbg = p->d_timeline;
-    const bool timeline = p->d_timeline != nullptr;
+    // results that land inside the registered symmetric region are stored into every rank's copy of it
+    const char *dstc = reinterpret_cast<const char *>(dst);
+    const bool push = p->push.n > 0 && dstc >= p->push.local && dstc + size_t(batch) * p->N * sizeof(double) <= p->push.local + p->push.bytes;
+    const bool timeline = p->d_timeline != nullptr && !push;
     const int rows = 2;  // rows folded side by side
     const int modekind = mode == kLowerMatvec ? (spec.fma ? 1 : 0) : mode == kUpperMatvec ? (spec.fma ? 3 : 2) : 4;
     const int shape = (W.h.threads == 384 ? 0 : 1) + (W.h.fibres == 2 ? (W.h.seq ? 6 : 2) : 0);  // < 8
-    const int key = ((cap / 8 - 1) * 5 + modekind) * 8 + shape + (timeline ? 160 : 0);                               // < 320
+    const int key = ((cap / 8 - 1) * 5 + modekind) * 8 + shape + (timeline ? 160 : 0) + (push ? 512 : 0);  // < 320 (+ 512 for the push variants)
     const int fibres_code = W.h.fibres == 2 ? (W.h.seq ? 3 : 2) : 1;
     const bool set_attr = !p->whole_attr_set[key];
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
         a.in = src + b0 * p->N; a.out = dst + b0 * p->N; a.batch = nb;
+        if (push) {
+            const int64_t off = (dstc - p->push.local) + b0 * p->N * int64_t(sizeof(double));
+            a.n_peers = p->push.n;
+            for (int r = 0; r < p->push.n; ++r) a.peer_out[r] = reinterpret_cast<double *>(p->push.peer[r] + off);
+            a.mc_out = p->push.mc ? reinterpret_cast<double *>(p->push.mc + off) : nullptr;
+        }
         const int per_sm = (W.h.threads == 384 && W.h.fibres == 1 && W.smem_bytes <= size_t(kWholeSmemPerCta)) ? 2 : 1;
         const int grid = int(std::min<int64_t>(nb, int64_t(per_sm) * p->num_sms));
         cudaError_t e = cudaSuccess;
@@ -614,6 +625,14 @@ int run_device(lpfnt_plan *p, const SweepSpec &spec, const std::vector<int> &dim
     scatter = scatter && p->has_perm;
     if (dims.empty()) { set_error("no sweep dimensions"); return LPFNT_EINVAL; }
     if (gather && dims[0] != 0) { set_error("gather requires a sweep along coordinate 0"); return LPFNT_EINVAL; }
+    {
+        const char *oc = reinterpret_cast<const char *>(out);
+        const bool in_push = p->push.n > 0 && oc >= p->push.local && oc < p->push.local + p->push.bytes;
+        if (in_push) {
+            if (!whole_ok(p, spec, dims, in, batch)) { set_error("output lies in the push region, but this call does not run on the whole-function kernel (the only kernel that stores into the peers' buffers)"); return LPFNT_EUNSUPPORTED; }
+            return launch_whole_fn(p, spec, in, out, batch, gather, scatter, s);
+        }
+    }
     if (wsplit_ok(p, spec, dims, in, batch)) return launch_wsplit_fn(p, spec, in, out, batch, gather, scatter, s);
     if (whole_ok(p, spec, dims, in, batch)) {
         // in-place is safe: a function is complete in shared memory / registers before its first store
@@ -946,6 +965,55 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         if (e != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(LPFNT_ECUDA); }
     }
     *plan = p;
+    return LPFNT_OK;
+}
+
+int lpfnt_plan_set_push(lpfnt_plan *p, const void *local_base, int64_t bytes, int n_peers, const void *const *peer_bases, const void *mc_base) {
+    if (!p) { set_error("null plan"); return LPFNT_EINVAL; }
+    if (n_peers == 0 || !local_base) { p->push = lpfnt_plan::Push(); return LPFNT_OK; }
+    if (n_peers < 1 || n_peers > 8 || bytes <= 0 || !peer_bases) { set_error("set_push: need 1..8 peer mappings and a region size"); return LPFNT_EINVAL; }
+    p->push.local = static_cast<const char *>(local_base);
+    p->push.bytes = bytes;
+    p->push.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_bases[r]) { set_error("set_push: null peer mapping"); return LPFNT_EINVAL; }
+        p->push.peer[r] = static_cast<char *>(const_cast<void *>(peer_bases[r]));
+    }
+    p->push.mc = static_cast<char *>(const_cast<void *>(mc_base));
+    return LPFNT_OK;
+}
+
+int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, void *stream) {
+    if (!src || bytes <= 0 || (bytes & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || n_dst < 0 || n_dst > 8 || (n_dst > 0 && !dst) || (n_dst == 0 && !mc_dst)) {
+        set_error("push_rows: need a 16-byte aligned source, a multiple of 16 bytes and 1..8 destinations or a multicast mapping");
+        return LPFNT_EINVAL;
+    }
+    CK(cudaSetDevice(device));
+    PushArgs a{};
+    a.src = static_cast<const uint4 *>(src);
+    a.words = bytes / 16;
+    a.mc = static_cast<uint4 *>(mc_dst);
+    for (int r = 0; r < n_dst; ++r) {
+        if (!dst[r] || (reinterpret_cast<uintptr_t>(dst[r]) & 15)) { set_error("push_rows: destinations must be 16-byte aligned"); return LPFNT_EINVAL; }
+        if (dst[r] != src) a.dst[a.n_dst++] = static_cast<uint4 *>(dst[r]);  // the own mapping already holds the rows
+    }
+    if (!a.mc && a.n_dst == 0) return LPFNT_OK;
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 148;  // (cudaGetDeviceProperties takes milliseconds)
+    const int grid = int(std::min<int64_t>((a.words + 255) / 256, int64_t(sms) * 4));
+    cudaError_t e = launch_push_rows(a, grid, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { set_error(std::string("push_rows launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
+    return LPFNT_OK;
+}
+
+int lpfnt_push_rows_ce(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *stream) {
+    if (!src || bytes <= 0 || n_dst < 1 || n_dst > 8 || !dst) { set_error("push_rows_ce: bad arguments"); return LPFNT_EINVAL; }
+    CK(cudaSetDevice(device));
+    for (int r = 0; r < n_dst; ++r) {
+        if (!dst[r]) { set_error("push_rows_ce: null destination"); return LPFNT_EINVAL; }
+        if (dst[r] == src) continue;  // the own mapping already holds the rows
+        CK(cudaMemcpyAsync(dst[r], src, size_t(bytes), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    }
     return LPFNT_OK;
 }
 

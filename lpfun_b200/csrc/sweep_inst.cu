@@ -28,15 +28,17 @@ cudaError_t group_launch(const GroupSweepArgs &a, const PackedTri<T> &M, int bat
     return cudaGetLastError();
 }
 
-template <int MODE, bool FMA, int TG, int ROWS, int NF = 1, bool SEQ = false, int MINB = 1, bool TL = false>
+template <int MODE, bool FMA, int TG, int ROWS, int NF = 1, bool SEQ = false, int MINB = 1, bool TL = false, bool PUSH = false>
 cudaError_t whole_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, size_t smem, bool set_attr, cudaStream_t s) {
-    auto kern = k_whole<T, MODE, FMA, TG, ROWS, NF, SEQ, MINB, TL>;
+    auto kern = k_whole<T, MODE, FMA, TG, ROWS, NF, SEQ, MINB, TL, PUSH>;
     if (set_attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
     }
     kern<<<grid, TG, smem, s>>>(a, M);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && std::getenv("LPFNT_DEBUG_OCCUPANCY")) std::fprintf(stderr, "k_whole<%d, mode %d, fma %d, %d thr, NF %d, push %d> launch: %s (grid %d, smem %zu)\n", T, MODE, int(FMA), TG, NF, int(PUSH), cudaGetErrorString(e), grid, smem);
+    return e;
 }
 // one fibre per thread: 768 threads, or 384 with the register budget of two CTAs per SM
 template <int MODE, bool FMA, int ROWS>
@@ -63,6 +65,22 @@ cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibre
     PackedTri<T> M;
     std::memcpy(M.v, tri, sizeof(M.v));
     if (threads != 384 && threads != 768) return cudaErrorInvalidValue;
+    if (a.n_peers > 0) {
+        // result pushed into every rank's symmetric buffer: the two default shapes of the lower mat-vec at the large capacities
+#if LPFNT_MAXT >= 24
+        if (mode == kLowerMatvec && fibres == 2 && threads == 384 && !timeline)
+            return fma ? whole_launch<kLowerMatvec, true, 384, 2, 2, false, 1, false, true>(a, M, grid, smem, set_attr, s)
+                       : whole_launch<kLowerMatvec, false, 384, 2, 2, false, 1, false, true>(a, M, grid, smem, set_attr, s);
+        if (mode == kLowerMatvec && fibres == 1 && threads == 768 && !timeline)
+            return fma ? whole_launch<kLowerMatvec, true, 768, 2, 1, false, 1, false, true>(a, M, grid, smem, set_attr, s)
+                       : whole_launch<kLowerMatvec, false, 768, 2, 1, false, 1, false, true>(a, M, grid, smem, set_attr, s);
+        if (mode == kLowerMatvec && fibres == 1 && threads == 384 && !timeline)
+            return fma ? whole_launch<kLowerMatvec, true, 384, 2, 1, false, 2, false, true>(a, M, grid, smem, set_attr, s)
+                       : whole_launch<kLowerMatvec, false, 384, 2, 1, false, 2, false, true>(a, M, grid, smem, set_attr, s);
+#endif
+        if (std::getenv("LPFNT_DEBUG_OCCUPANCY")) std::fprintf(stderr, "launch_whole<%d>: no push variant for mode %d fma %d threads %d fibres %d timeline %d\n", T, mode, int(fma), threads, fibres, int(timeline));
+        return cudaErrorNotSupported;
+    }
     if (fibres == 2) {
         if (mode != kLowerMatvec || threads != 384) return cudaErrorInvalidValue;
         return fma ? whole_launch_two<kLowerMatvec, true, false>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, false>(timeline, a, M, grid, smem, set_attr, s);
@@ -166,6 +184,11 @@ cudaError_t launch_line_sweep<T>(int mode, bool fma, const LineSweepArgs &a, con
 cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int batch, bool restrict_, cudaStream_t s) {
     dim3 grid(unsigned((n_small + 255) / 256), batch);
     k_embed<<<grid, 256, 0, s>>>(in, out, phi, n_small, n_big, restrict_ ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_push_rows(const PushArgs &a, int grid, cudaStream_t s) {
+    k_push_rows<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

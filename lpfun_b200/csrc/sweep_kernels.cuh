@@ -470,7 +470,32 @@ __device__ __forceinline__ double mac_rt(double acc, double a, double b, int fma
     return fma ? __fma_rn(a, b, acc) : __dadd_rn(acc, __dmul_rn(a, b));
 }
 
+// Row blocks of a result pushed into the other ranks' copies of a symmetric buffer over NVLink (the all-gather of a batch
+// sharded by rows as a plain streaming copy: 16-byte loads from local HBM, 16-byte stores into every peer mapping, or ONE
+// multimem.st.v4 through the NVSwitch multicast mapping, which reaches every GPU).  Grid-stride over 16-byte words.
+struct PushArgs {
+    const uint4 *src;
+    uint4 *dst[8];
+    uint4 *mc;       // multicast mapping (or nullptr)
+    int64_t words;   // 16-byte words
+    int32_t n_dst;
+};
+__global__ void __launch_bounds__(256) k_push_rows(const PushArgs a);
+
 #if defined(LPFNT_MAXT) && LPFNT_MAXT == 8  // defined once, in the MAXT=8 translation unit
+__global__ void __launch_bounds__(256) k_push_rows(const PushArgs a) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < a.words; i += stride) {
+        const uint4 v = __ldcs(a.src + i);
+        if (a.mc) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + i), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                         "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                         : "memory");
+        } else {
+            for (int r = 0; r < a.n_dst; ++r) a.dst[r][i] = v;
+        }
+    }
+}
 __global__ void __launch_bounds__(256) k_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int scatter) {
     const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= n) return;

@@ -29,6 +29,7 @@ cudaError_t launch_whole(int mode, bool fma, int threads, int rows, int fibres, 
 template <int MAXT>
 cudaError_t launch_whole_split(bool fma, bool timeline, const WholeSplitArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s);
 
+cudaError_t launch_push_rows(const PushArgs &a, int grid, cudaStream_t s);
 cudaError_t launch_permute(const double *x, double *y, const int32_t *perm, int64_t n, int64_t stride, int batch, bool scatter, cudaStream_t s);
 cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int64_t n_small, int64_t n_big, int batch, bool restrict_, cudaStream_t s);
 cudaError_t launch_generic_sweep(const GenericArgs &a, int batch, cudaStream_t s);

@@ -47,6 +47,12 @@ struct WholeArgs {
     const uint16_t *seo;               // per coordinate h >= 1 the line offsets in fibre order
     const uint16_t *perm16;            // colex permutation (or nullptr)
     long long *dbg;                    // development: clock64 stamps (nullptr in production)
+    // PUSH instantiations: the result is stored into the SAME offset of every rank's copy of a symmetric buffer (an all-gather
+    // done by the last sweep's stores, over NVLink): through the NVSwitch multicast mapping when there is one (one
+    // multimem.st reaches every GPU, the own one included), else by one plain store per peer mapping
+    double *mc_out;                    // multicast mapping of `out` (or nullptr)
+    double *peer_out[8];               // peer mappings of `out`, the own one included (n_peers entries)
+    int32_t n_peers;
     int32_t item_off[3], n_items[3];
     int32_t total_items, seo_len;
     int32_t gather, scatter;
@@ -79,6 +85,9 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
                      static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))),
                  "l"(gsrc), "r"(bytes), "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar)))
                  : "memory");
+}
+__device__ __forceinline__ void multimem_st_f64(double *mc_addr, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc_addr), "d"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -126,7 +135,7 @@ __device__ __forceinline__ void apply_fibre2(double (&x)[MAXT], double (&y)[MAXT
 // registers of a 384-thread CTA let ptxas keep the two row chains of the exact form interleaved (at the 80 registers of
 // a 768-thread CTA it emits ONE serial DMUL -> DADD chain per warp: half the rate once a warp runs alone).
 // MINB: CTAs per SM the register budget is cut for.
-template <int MAXT, int MODE, bool FMA, int TG, int ROWS, int NF = 1, bool SEQ = false, int MINB = 1, bool TL = false>
+template <int MAXT, int MODE, bool FMA, int TG, int ROWS, int NF = 1, bool SEQ = false, int MINB = 1, bool TL = false, bool PUSH = false>
 __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ WholeArgs a, const __grid_constant__ PackedTri<MAXT> M) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *const buf0 = reinterpret_cast<double *>(smem_raw);  // 16-byte aligned landing zone
@@ -281,6 +290,17 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
                         const uint2 *eo4 = reinterpret_cast<const uint2 *>(W_SEO + (it & 0xffffu));
                         const unsigned add = it >> 22;
                         double *out = a.out + int64_t(b) * N;
+                        // one result element -> out[idx] (PUSH: the same offset on every rank)
+                        auto put = [&](unsigned idx, double v) {
+                            if constexpr (PUSH) {
+                                const int64_t o = int64_t(b) * N + idx;
+                                if (a.mc_out) multimem_st_f64(a.mc_out + o, v);
+                                else
+                                    for (int r = 0; r < a.n_peers; ++r) a.peer_out[r][o] = v;
+                            } else {
+                                out[idx] = v;
+                            }
+                        };
                         if (a.scatter) {
                             // blocks of eight rows: offsets (two loads), permutation look-ups (eight independent loads),
                             // stores -- one dependent chain per block instead of one per element
@@ -294,16 +314,16 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
                                 for (int j = 0; j < 8; ++j) u[j] = (k8 + j < t2) ? W_SPERM[o[j] + add] : 0u;  // rows past the fibre hold padding
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
-                                    if (k8 + j < t2) out[u[j]] = x[f][k8 + j];
+                                    if (k8 + j < t2) put(u[j], x[f][k8 + j]);
                             }
                         } else {
 #pragma unroll
                             for (int k4 = 0; k4 < MAXT; k4 += 4) {
                                 const uint2 e = eo4[k4 >> 2];
-                                if (k4 < t2) out[(e.x & 0xffffu) + add] = x[f][k4];
-                                if (k4 + 1 < t2) out[(e.x >> 16) + add] = x[f][k4 + 1];
-                                if (k4 + 2 < t2) out[(e.y & 0xffffu) + add] = x[f][k4 + 2];
-                                if (k4 + 3 < t2) out[(e.y >> 16) + add] = x[f][k4 + 3];
+                                if (k4 < t2) put((e.x & 0xffffu) + add, x[f][k4]);
+                                if (k4 + 1 < t2) put((e.x >> 16) + add, x[f][k4 + 1]);
+                                if (k4 + 2 < t2) put((e.y & 0xffffu) + add, x[f][k4 + 2]);
+                                if (k4 + 3 < t2) put((e.y >> 16) + add, x[f][k4 + 3]);
                             }
                         }
                     } else {

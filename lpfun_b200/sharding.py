@@ -52,6 +52,96 @@ def gather_rows(local, total: int, group=None):
     return torch.cat(pieces, dim=0)
 
 
+class PushGather:
+    """All-gather of the row blocks of a sharded batch WITHOUT a collective: the full (total, N) result lives in a symmetric
+    buffer (``torch.distributed._symmetric_memory``) that every rank maps -- also through the NVSwitch multicast mapping
+    when the fabric offers one -- and the whole-function kernel stores every result element of this rank's rows into the same
+    offset of every rank's copy (``lpfnt_plan_set_push``): one ``multimem.st`` per element, or one store per peer over NVLink.
+    The ranks only synchronise afterwards (:meth:`barrier`).
+
+        pg = PushGather(t, total_rows)           # collective: every rank calls it
+        t.ifnt(coef_block, out=pg.local_rows())  # this rank's rows -> every rank's buffer
+        pg.barrier(); full = pg.full             # (total, N) on every rank
+    """
+
+    def __init__(self, t, total: int, group=None, use_multicast: bool = True, fused: bool = True):
+        """fused=True registers the buffer with the plan (the whole-function kernel stores into every rank's copy);
+        fused=False leaves the kernels alone: write ``out=local_rows()`` as usual, then :meth:`push_rows` (a streaming copy
+        kernel on a stream of your choice) sends row ranges to the other ranks."""
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _native as nat
+
+        if dist is None or not dist.is_initialized():
+            raise RuntimeError("PushGather needs an initialised torch.distributed process group")
+        self.t, self.total = t, int(total)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PushGather: at most 8 ranks (one NVSwitch domain)")
+        N = len(t)
+        dev = torch.device("cuda", t.device)
+        self.full = symm_mem.empty((self.total, N), dtype=torch.float64, device=dev)
+        self.hdl = symm_mem.rendezvous(self.full, self.group)
+        peers = [int(p) for p in self.hdl.buffer_ptrs]
+        # the handle's pointers address the allocation; the tensor may sit at an offset inside it
+        off = int(self.hdl.offset) if hasattr(self.hdl, "offset") else 0
+        base = self.full.data_ptr()
+        if peers[self.rank] + off != base:
+            off = base - peers[self.rank]
+        mc = int(self.hdl.multicast_ptr) if (use_multicast and self.hdl.has_multicast_support) else 0
+        self.multicast = mc != 0
+        arr = (C.c_void_p * self.world)(*[p + off for p in peers])
+        nbytes = self.total * N * 8
+        self._peer_bases = [p + off for p in peers]
+        self._mc_base = mc + off if mc else 0
+        self._row_bytes = N * 8
+        self.fused = bool(fused)
+        if self.fused:
+            nat.check(nat.lib().lpfnt_plan_set_push(t._plan, C.c_void_p(base), nbytes, self.world, arr, C.c_void_p(mc + off if mc else 0)))
+        self._a, self._b = row_block(self.total, self.rank, self.world)
+
+    def local_rows(self):
+        """This rank's rows of the full result (pass as ``out=``)."""
+        return self.full[self._a:self._b]
+
+    def push_rows(self, lo: int, hi: int, stream=None, engine: str = "sm"):
+        """Send the rows [lo, hi) of THIS rank's block (already written into its own copy) to every other rank's copy:
+        engine="sm" a streaming copy kernel (multimem.st.v4 when the buffer has a multicast mapping), engine="ce" the copy
+        engines (they need no SM, so the transfer overlaps the persistent sweep kernels)."""
+        import ctypes as C
+
+        from . import _native as nat
+
+        if not (0 <= lo <= hi <= self._b - self._a):
+            raise ValueError("push_rows: row range outside this rank's block")
+        if hi == lo:
+            return
+        s = stream if stream is not None else torch.cuda.current_stream(self.full.device)
+        first = (self._a + lo) * self._row_bytes
+        nbytes = (hi - lo) * self._row_bytes
+        dst = (C.c_void_p * self.world)(*[b + first for b in self._peer_bases])
+        if engine == "ce":
+            nat.check(nat.lib().lpfnt_push_rows_ce(self.t.device, C.c_void_p(self._peer_bases[self.rank] + first), nbytes, self.world, dst,
+                                                   C.c_void_p(s.cuda_stream)))
+            return
+        mc = C.c_void_p(self._mc_base + first) if self._mc_base else C.c_void_p(0)
+        nat.check(nat.lib().lpfnt_push_rows(self.t.device, C.c_void_p(self._peer_bases[self.rank] + first), nbytes,
+                                            0 if self._mc_base else self.world, dst, mc, C.c_void_p(s.cuda_stream)))
+
+    def barrier(self):
+        """Every rank's stores have landed everywhere (device-side barrier on the current stream)."""
+        self.hdl.barrier()
+
+    def close(self):
+        from . import _native as nat
+
+        if self.fused:
+            nat.check(nat.lib().lpfnt_plan_set_push(self.t._plan, None, 0, 0, None, None))
+
+
 def sharded_apply(fn, full_rows, group=None, gather: bool = True):
     """Apply ``fn`` (e.g. ``t.fnt``) to this rank's block of ``full_rows`` and optionally all-gather."""
     if dist is None or not dist.is_initialized():

@@ -485,6 +485,36 @@ def _run_sharded(world):
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def _run_push(world):
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_push_gpu.py")
+    if world == 1:
+        cmd = [sys.executable, script]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", "29543", script]
+    env = dict(os.environ)
+    env.pop("RANK", None); env.pop("WORLD_SIZE", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "PUSH_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_push_gather_one_gpu():
+    """The whole-function kernel storing its result into the symmetric buffer (a world of one: the own mapping only)."""
+    _run_push(1)
+
+
+def test_push_gather_two_gpus():
+    """Row blocks of a sharded batch gathered by the last sweep's stores into every rank's buffer (multimem.st / peer stores)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    _run_push(2)
+
+
 def test_sharded_single_transform_one_gpu():
     """Slab sweeps -> all-to-all -> column sweep on a process group of one (NCCL): bit-identical to the plain transform."""
     _run_sharded(1)
