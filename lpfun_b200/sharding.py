@@ -124,8 +124,18 @@ class PushGather:
         nbytes = (hi - lo) * self._row_bytes
         dst = (C.c_void_p * self.world)(*[b + first for b in self._peer_bases])
         if engine == "ce":
-            nat.check(nat.lib().lpfnt_push_rows_ce(self.t.device, C.c_void_p(self._peer_bases[self.rank] + first), nbytes, self.world, dst,
-                                                   C.c_void_p(s.cuda_stream)))
+            # one stream per peer: the copies to different peers run on different copy engines at the same time
+            if not hasattr(self, "_peer_streams"):
+                self._peer_streams = [torch.cuda.Stream(self.full.device) for _ in range(self.world)]
+            src = C.c_void_p(self._peer_bases[self.rank] + first)
+            for q in range(1, self.world):
+                r = (self.rank + q) % self.world  # every rank starts with another peer
+                ps = self._peer_streams[r]
+                ps.wait_stream(s)
+                one = (C.c_void_p * 1)(self._peer_bases[r] + first)
+                nat.check(nat.lib().lpfnt_push_rows_ce(self.t.device, src, nbytes, 1, one, C.c_void_p(ps.cuda_stream)))
+            for q in range(1, self.world):
+                s.wait_stream(self._peer_streams[(self.rank + q) % self.world])
             return
         mc = C.c_void_p(self._mc_base + first) if self._mc_base else C.c_void_p(0)
         nat.check(nat.lib().lpfnt_push_rows(self.t.device, C.c_void_p(self._peer_bases[self.rank] + first), nbytes,
