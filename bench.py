@@ -438,13 +438,13 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
     # the same step with OUR OWN gather over NVLink peer memory (lpfun_b200.sharding.PushGather, a symmetric buffer):
     #   copy_engine: chunk k goes to the other ranks' copies by the copy engines (cudaMemcpyAsync to the peer mappings) on a side
     #             stream while chunk k+1 is swept -- no SM is taken from the persistent sweep kernels;
-    #   copy_*  : the same with a streaming copy kernel (lpfnt_push_rows): 16-byte stores per peer mapping, or ONE multimem.st.v4
-    #             through the NVSwitch multicast (the sweep kernels fill the SMs, so this one only runs between them);
+    #   copy_*  : the same with a streaming copy kernel (lpfnt_push_rows, one 128-thread CTA per SM): 16-byte stores per peer
+    #             mapping, or ONE multimem.st.v4 through the NVSwitch multicast;
     #   fused_* : k_whole itself stores every reconstruction into the same offset of every rank's copy (lpfnt_plan_set_push).
     # The ranks only synchronise afterwards (signal-pad barrier).
     push = None
     if world > 1:
-        from lpfun_b200.sharding import PushGather
+        from lpfun_b200.sharding import PushGather, plan_push_chunks
 
         push = {}
         for mode in ("copy_engine", "copy_peer_stores", "copy_multicast", "fused_peer_stores", "fused_multicast"):
@@ -455,21 +455,25 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
                     pg.close()
                     continue
                 mine = pg.local_rows()
-                # chunks in whole rounds of the persistent sweep kernel (multiples of the SM count), the last one short: its
-                # transfer is the only one that nothing hides
+                eng = "ce" if mode == "copy_engine" else "sm"
+                # chunks in whole rounds of the persistent sweep kernel, cut by the pipeline model of plan_push_chunks from the
+                # two times measured above (sweeps alone, NCCL gather alone as the estimate of the link time per row)
                 sms = torch.cuda.get_device_properties(dev).multi_processor_count
                 rounds = -(-Bl // sms)
-                r_last = max(1, rounds // 5)
-                r_rest = rounds - r_last
-                cuts = [0]
-                for q in range(2):
-                    if r_rest > 0:
-                        take = (r_rest + (1 - q)) // 2 if q == 0 else r_rest - (r_rest + 1) // 2
-                        if take > 0:
-                            cuts.append(min(Bl, cuts[-1] + take * sms))
-                if cuts[-1] < Bl:
-                    cuts.append(Bl)
-                bounds = list(zip(cuts[:-1], cuts[1:]))
+                ms_copy = None
+                if not fused:  # this engine's own time for the whole block, every rank sending at once
+                    for _ in range(2):
+                        pg.push_rows(0, Bl, engine=eng)
+                    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record()
+                    for _ in range(K):
+                        pg.push_rows(0, Bl, engine=eng)
+                    c1.record(); torch.cuda.synchronize()
+                    tc = torch.tensor([c0.elapsed_time(c1) / K], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+                    ms_copy = float(tc.item())
+                bounds = plan_push_chunks(Bl, sms, ms_sweeps / rounds, (ms_copy if ms_copy else ms_gather) / max(1, Bl))
 
                 def step_push():
                     if fused:  # the last sweep's stores go to every rank
@@ -479,7 +483,7 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
                             sl = slice(lo, hi)
                             t.fnt(vals[sl], out=coef[sl]); t.ifnt(coef[sl], out=mine[sl])
                             comm.wait_stream(torch.cuda.current_stream(dev))
-                            pg.push_rows(lo, hi, stream=comm, engine="ce" if mode == "copy_engine" else "sm")
+                            pg.push_rows(lo, hi, stream=comm, engine=eng)
                         torch.cuda.current_stream(dev).wait_stream(comm)
                     pg.barrier()
 
@@ -501,6 +505,7 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
                 push[mode] = {"ms_per_step": float(tt.item()), "GDOF_s": 2.0 * N * Btot / (float(tt.item()) * 1e-3) / 1e9, "gather_checked": good}
                 if not fused:
                     push[mode]["chunks"] = [hi - lo for lo, hi in bounds]
+                    push[mode]["ms_copy_only"] = ms_copy
                 pg.close()
                 del pg, mine
                 torch.cuda.empty_cache()
@@ -512,7 +517,7 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
     best_ms, how = ms, ("ncclAllGather on a side stream" if world > 1 else "none (one rank)")
     if push:
         names = {"copy_engine": "own gather: copy engines store chunk k into the peers' mappings of a symmetric buffer (NVLink) behind the sweeps of chunk k+1",
-                 "copy_peer_stores": "own gather: streaming copy kernel, 16-byte stores into the peers' mappings (NVLink)",
+                 "copy_peer_stores": "own gather: streaming copy kernel (one small CTA per SM beside the sweep CTAs), 16-byte stores into the peers' mappings (NVLink)",
                  "copy_multicast": "own gather: streaming copy kernel, multimem.st.v4 through the NVSwitch multicast mapping",
                  "fused_peer_stores": "own gather fused into k_whole: the last sweep stores into every peer's mapping",
                  "fused_multicast": "own gather fused into k_whole: multimem.st through the NVSwitch multicast mapping"}

@@ -1000,7 +1000,10 @@ int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void 
     if (!a.mc && a.n_dst == 0) return LPFNT_OK;
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 148;  // (cudaGetDeviceProperties takes milliseconds)
-    const int grid = int(std::min<int64_t>((a.words + 255) / 256, int64_t(sms) * 4));
+    // ONE small CTA per SM: it fits beside the persistent sweep CTA (4096 registers are left); two would keep the next sweep
+    // CTA out of the SM until the copy has finished
+    static const int per_sm = [] { const char *v = std::getenv("LPFNT_DEBUG_PUSH_CTAS"); return v ? std::max(1, atoi(v)) : 1; }();
+    const int grid = int(std::min<int64_t>((a.words + 127) / 128, int64_t(sms) * per_sm));
     cudaError_t e = launch_push_rows(a, grid, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { set_error(std::string("push_rows launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
     return LPFNT_OK;

@@ -188,7 +188,14 @@ cudaError_t launch_embed(const double *in, double *out, const int64_t *phi, int6
 }
 
 cudaError_t launch_push_rows(const PushArgs &a, int grid, cudaStream_t s) {
-    k_push_rows<<<grid, 256, 0, s>>>(a);
+    static const int carve = [] {
+        const char *v = std::getenv("LPFNT_DEBUG_PUSH_CARVEOUT");
+        const int c = v ? atoi(v) : -1;
+        if (c >= 0) cudaFuncSetAttribute(k_push_rows, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        return c;
+    }();
+    (void)carve;
+    k_push_rows<<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -480,12 +480,30 @@ struct PushArgs {
     int64_t words;   // 16-byte words
     int32_t n_dst;
 };
-__global__ void __launch_bounds__(256) k_push_rows(const PushArgs a);
+__global__ void __launch_bounds__(128, 16) k_push_rows(const PushArgs a);
 
 #if defined(LPFNT_MAXT) && LPFNT_MAXT == 8  // defined once, in the MAXT=8 translation unit
-__global__ void __launch_bounds__(256) k_push_rows(const PushArgs a) {
+// 128 threads and <= 32 registers per thread: one such CTA fits next to the persistent sweep CTA of an SM (768 x 80 or
+// 384 x 160 registers leave 4096), so the copy of chunk k can run while chunk k+1 is swept.
+__global__ void __launch_bounds__(128, 16) k_push_rows(const PushArgs a) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < a.words; i += stride) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < a.words; i += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(a.src + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (a.mc) {
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + i + u * stride), "f"(__uint_as_float(v[u].x)),
+                             "f"(__uint_as_float(v[u].y)), "f"(__uint_as_float(v[u].z)), "f"(__uint_as_float(v[u].w))
+                             : "memory");
+            } else {
+                for (int r = 0; r < a.n_dst; ++r) a.dst[r][i + u * stride] = v[u];
+            }
+        }
+    }
+    for (; i < a.words; i += stride) {
         const uint4 v = __ldcs(a.src + i);
         if (a.mc) {
             asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + i), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),

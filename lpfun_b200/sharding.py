@@ -52,6 +52,52 @@ def gather_rows(local, total: int, group=None):
     return torch.cat(pieces, dim=0)
 
 
+def plan_push_chunks(rows: int, rows_per_round: int, sweep_ms_per_round: float, copy_ms_per_row: float,
+                     launch_ms: float = 0.008, max_chunks: int = 5):
+    """Cut this rank's `rows` functions into chunks for a pipelined gather: chunk k is copied to the peers on a side stream while
+    chunk k+1 is swept.  Chunks are whole rounds of the persistent sweep kernel (`rows_per_round` = one function per SM).  The
+    cut minimises the modelled end of the last copy: a sweep of r rounds takes r * sweep_ms_per_round + launch_ms, a copy of n
+    rows n * copy_ms_per_row + launch_ms, copies run one after another.  When the sweeps dominate the chunks shrink
+    geometrically (only the last, small copy is exposed); when the copies dominate the first chunk is one round (the link
+    starts early) and the rest is sent in few large pieces.  Returns [(lo, hi), ...]."""
+    if rows <= 0:
+        return []
+    rounds = -(-rows // rows_per_round)
+    best, best_cut = None, None
+
+    def finish(parts):
+        t_sweep = t_copy = 0.0
+        done = 0
+        for r in parts:
+            n = min(rows, (done + r) * rows_per_round) - done * rows_per_round
+            t_sweep += r * sweep_ms_per_round + launch_ms
+            t_copy = max(t_copy, t_sweep) + n * copy_ms_per_row + launch_ms
+            done += r
+        return t_copy
+
+    def rec(left, parts):
+        nonlocal best, best_cut
+        if left == 0:
+            f = finish(parts)
+            if best is None or f < best - 1e-12:
+                best, best_cut = f, list(parts)
+            return
+        if len(parts) == max_chunks - 1:
+            rec(0, parts + [left])
+            return
+        for r in range(1, left + 1):
+            rec(left - r, parts + [r])
+
+    rec(rounds, [])
+    out, done = [], 0
+    for r in best_cut:
+        lo, hi = done * rows_per_round, min(rows, (done + r) * rows_per_round)
+        if hi > lo:
+            out.append((lo, hi))
+        done += r
+    return out
+
+
 class PushGather:
     """All-gather of the row blocks of a sharded batch WITHOUT a collective: the full (total, N) result lives in a symmetric
     buffer (``torch.distributed._symmetric_memory``) that every rank maps -- also through the NVSwitch multicast mapping

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lpfun_b200.sharding import gather_rows, row_block, sharded_apply
+from lpfun_b200.sharding import gather_rows, plan_push_chunks, row_block, sharded_apply
 
 
 def test_row_block_partitions():
@@ -21,6 +21,23 @@ def test_row_block_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         row_block(4, 2, 2)
+
+
+def test_plan_push_chunks_covers_rows_in_whole_rounds():
+    for rows in (0, 1, 100, 148, 512, 2048, 2049):
+        for sweep, copy in ((0.045, 0.00015), (0.057, 0.0012), (0.05, 0.0)):
+            cuts = plan_push_chunks(rows, 148, sweep, copy)
+            if rows == 0:
+                assert cuts == []
+                continue
+            assert cuts[0][0] == 0 and cuts[-1][1] == rows and len(cuts) <= 5
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert all(lo % 148 == 0 and hi > lo for lo, hi in cuts)
+    # sweeps dominate: the last chunk (the only exposed copy) is the smallest; copies dominate: the first chunk is one round
+    cuts = plan_push_chunks(2048, 148, 0.045, 0.00015)
+    assert cuts[-1][1] - cuts[-1][0] == min(hi - lo for lo, hi in cuts) and len(cuts) >= 3
+    cuts = plan_push_chunks(512, 148, 0.057, 0.0012)
+    assert cuts[0] == (0, 148)
 
 
 def _free_port():
