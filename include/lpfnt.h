@@ -108,8 +108,8 @@ enum {
 int lpfnt_index_create(const int64_t *A, int64_t N, int m, int n, lpfnt_index **index);
 int lpfnt_index_destroy(lpfnt_index *index);
 /* Item tables of the whole-function kernel (m = 2, 3; N < 65536).  lpfnt_index_whole_build re-builds them for CTAs of
- * `threads` threads (384 or 768), `fibres` (1 item per thread and round; 2: two of equal length class, folded side by side;
- * 3: a long and a short one, folded one after the other) and an item order (2 bits per coordinate, 0 strict length order,
+ * `threads` threads (384 or 768), `fibres` (1 item per thread and round; 2: two of equal length class, folded side by
+ * side) and an item order (2 bits per coordinate, 0 strict length order,
  * 1 / 2 classes of 8 / 16 rows, 3 natural; + 64: chunks of 32 items dealt to the warps by a model of the shared FP64 pipe
  * instead of the snake order over the four SM sub-partitions; < 0 = default).  lpfnt_index_whole_meta fills 10 int32: ok, threads,
  * longest item, most items of a list, {list offset, padded list length} per coordinate; returns the number written. */
@@ -176,8 +176,8 @@ int64_t lpfnt_plan_launch_count(const lpfnt_plan *plan);
  *          "use_whole" (whole function in shared memory, one pass over HBM per transform, m = 2, 3:
  *          -1 = automatic (default: batches of >= 8 functions), 0 = off, 1 = always),
  *          "whole_threads" / "whole_fibres" / "whole_order" (CTA shape of the whole-function kernel: 384 or 768 threads;
- *          1 item per thread, 2 = two of equal length class folded side by side, 3 = a long and a short one folded one
- *          after the other; item order, see lpfnt_index_whole_build; -1 = automatic; the suffixes "_exact" / "_fma"
+ *          1 item per thread, 2 = two of equal length class folded side by side; item order, see
+ *          lpfnt_index_whole_build; -1 = automatic; the suffixes "_exact" / "_fma"
  *          address the tables of the exact / the fused-multiply-add forms only),
  *          "whole_split" (m = 3: every function as two units -- planes a_2 < C and a_2 >= C -- so that two CTAs fit on an SM;
  *          0 = off (default: measured slower), 1 = on, -1 = automatic), "whole_split_c" (the split plane, 0 = balanced),

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "liblpfnt.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 GROUP_LANES = os.environ.get("LPFNT_GROUP_LANES")
-COMMON = ([f"-DLPFNT_GROUP_LANES={GROUP_LANES}"] if GROUP_LANES else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xfatbin=-compress-all", "-Xcompiler", "-fPIC"]
+COMMON = ([f"-DLPFNT_GROUP_LANES={GROUP_LANES}"] if GROUP_LANES else []) + (["-DLPFNT_TIMELINE_SPLIT"] if os.environ.get("LPFNT_TIMELINE_SPLIT") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xfatbin=-compress-all", "-Xcompiler", "-fPIC"]
 
 # (source, object name, extra defines)
 UNITS = [
@@ -83,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for _, log in results:
             if log.strip():
                 print(log, file=sys.stderr)
-    link = [nvcc, *ccbin, *ARCH, "-shared", "-o", LIB, *objs]
+    link = [nvcc, *ccbin, *ARCH, "-shared", "-Xlinker", "-s", "-o", LIB, *objs]  # -s: no host symbol table (the exported C-ABI stays in .dynsym)
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{' '.join(link)}\n{r.stdout}\n{r.stderr}")

@@ -414,10 +414,9 @@ void free_whole(lpfnt_plan *p, int which) {
 // CTA shape: two CTAs of 384 threads (one fibre per thread) per SM when two functions (plus tables) fit into shared memory;
 // else one CTA per SM: the fused forms with 384 threads and TWO fibres each, folded side by side (every matrix entry feeds
 // two DFMA: the constant path, one LDCU.64 per ~4 cycles and SM sub-partition, is half as loaded: ifnt 0.53 -> 0.49 ms at
-// d = 3, n = 30, B = 4096), the exact forms with 768 threads and one fibre each.  Measured alternative for the exact
-// forms (fibres = 3): 384 threads with a long and a short item each, one after the other -- equal work per warp and
-// interleaved row chains bring the triangle phases to 88 % of the FP64 pipe (7.3 K cycles per sweep instead of 8.5-10 K),
-// but the load / store phases of 12 instead of 24 warps grow by more (0.69 vs 0.61 ms).
+// d = 3, n = 30, B = 4096), the exact forms with 768 threads and one fibre each.  (A third form -- 384 threads with a long
+// and a short item each, one after the other: equal work per warp, 88 % of the FP64 pipe in the triangle phases, but load /
+// store phases of 12 instead of 24 warps that grow by more, 0.69 vs 0.61 ms -- was measured and removed)
 int upload_whole(lpfnt_plan *p, int which) {
     lpfnt_plan::Whole &W = p->whole[which];
     const lpfnt_plan::WholeCfg &cfg = p->wcfg[which];
@@ -426,7 +425,7 @@ int upload_whole(lpfnt_plan *p, int which) {
     for (int pass = 0; pass < 2; ++pass) {
         int tg = cfg.threads, nf = cfg.fibres;
         if (pass == 0) { if (tg <= 0) tg = 384; if (nf <= 0) nf = 1; }
-        else { if (nf <= 0) nf = (tg == 768) ? 1 : (tg == 384 ? (which == 1 ? 2 : 3) : (which == 1 ? 2 : 1)); if (tg <= 0) tg = nf == 1 ? 768 : 384; }
+        else { if (nf <= 0) nf = (tg == 768) ? 1 : (which == 1 ? 2 : 1); if (tg <= 0) tg = nf == 1 ? 768 : 384; }
         if (nf >= 2) tg = 384;  // two fibres per thread: 168 registers, i.e. 384 threads
         p->hx->build_whole(tg, cfg.order, nf);
         const WholeHost &h = p->hx->whole;
@@ -481,9 +480,9 @@ int launch_whole_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, dou
     const bool timeline = p->d_timeline != nullptr && !push;
     const int rows = 2;  // rows folded side by side
     const int modekind = mode == kLowerMatvec ? (spec.fma ? 1 : 0) : mode == kUpperMatvec ? (spec.fma ? 3 : 2) : 4;
-    const int shape = (W.h.threads == 384 ? 0 : 1) + (W.h.fibres == 2 ? (W.h.seq ? 6 : 2) : 0);  // < 8
+    const int shape = (W.h.threads == 384 ? 0 : 1) + (W.h.fibres == 2 ? 2 : 0);  // < 8
     const int key = ((cap / 8 - 1) * 5 + modekind) * 8 + shape + (timeline ? 160 : 0) + (push ? 512 : 0);  // < 320 (+ 512 for the push variants)
-    const int fibres_code = W.h.fibres == 2 ? (W.h.seq ? 3 : 2) : 1;
+    const int fibres_code = W.h.fibres == 2 ? 2 : 1;
     const bool set_attr = !p->whole_attr_set[key];
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
@@ -567,7 +566,7 @@ bool wsplit_ok(const lpfnt_plan *p, const SweepSpec &spec, const std::vector<int
     for (int q = 0; q < 3; ++q) if (dims[q] != q) return false;
     if (sweep_mode(spec) != kLowerMatvec) return false;
     if (reinterpret_cast<uintptr_t>(in) & 15) return false;
-    if (pick_cap(std::max(W.h.max_t, 1)) < 24) return false;  // small functions fit twice into an SM unsplit
+    if (pick_cap(std::max(W.h.max_t, 1)) < 32) return false;  // smaller functions (n <= 23: N <= 7.3 K) fit twice into an SM unsplit
     // automatic: only when the unsplit kernel is limited to one CTA per SM, and for batches that fill the GPU
     if (p->use_whole_split == 1) return true;
     const lpfnt_plan::Whole &U = p->whole[spec.fma ? 1 : 0];
@@ -593,7 +592,7 @@ int launch_wsplit_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
     a.n_elem = int32_t(p->N);
     a.skew = p->whole_split_skew;
     const bool timeline = p->d_timeline != nullptr;
-    const int key = 400 + (cap == 32 ? 0 : 4) + (spec.fma ? 1 : 0) + (timeline ? 2 : 0);
+    const int key = 400 + (spec.fma ? 1 : 0) + (timeline ? 2 : 0);
     const bool set_attr = !p->whole_attr_set[key];
     for (int64_t b0 = 0; b0 < batch; b0 += (int64_t(1) << 30)) {
         const int nb = int(std::min<int64_t>(int64_t(1) << 30, batch - b0));
@@ -601,8 +600,7 @@ int launch_wsplit_fn(lpfnt_plan *p, const SweepSpec &spec, const double *src, do
         const int grid = int(std::min<int64_t>(nb, int64_t(2) * p->num_sms));
         cudaError_t e = cudaSuccess;
         trace_begin(p, 1500, s);
-        if (cap == 32) e = launch_whole_split<32>(spec.fma, timeline, a, tri, grid, W.smem_bytes, set_attr, s);
-        else e = launch_whole_split<24>(spec.fma, timeline, a, tri, grid, W.smem_bytes, set_attr, s);
+        e = cap == 32 ? launch_whole_split<32>(spec.fma, timeline, a, tri, grid, W.smem_bytes, set_attr, s) : cudaErrorInvalidValue;
         trace_end(p, s);
         p->launches += 1;
         if (e != cudaSuccess) { set_error(std::string("split whole-function kernel launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
@@ -1102,7 +1100,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
             for (int w = lo; w <= hi; ++w) {
                 lpfnt_plan::WholeCfg &c = p->wcfg[w];
                 if (key == "threads") c.threads = (value == 384 || value == 768) ? int(value) : -1;
-                else if (key == "fibres") c.fibres = (value >= 1 && value <= 3) ? int(value) : -1;
+                else if (key == "fibres") c.fibres = (value >= 1 && value <= 2) ? int(value) : -1;
                 else if (key == "order") c.order = value < 0 ? kWholeDefaultOrder : int(value & 127);
                 else c.rows = (value == 2 || value == 4) ? int(value) : -1;
             }

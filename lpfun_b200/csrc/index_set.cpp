@@ -355,13 +355,13 @@ struct WholeItem { int t; uint32_t w; };
 // Orders the items of one sweep (length classes, natural order inside a class) and appends them to `out` in THREAD order:
 // rounds of TG * NF slots, thread i owning slots i, TG + i; inside a round chunks of 32 items dealt to the warps.
 // Returns the padded list length.
-int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool model, int TG, int NF, bool seq, std::vector<uint32_t> &out) {
+int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool model, int TG, int NF, std::vector<uint32_t> &out) {
     const int RT = TG * NF;
     const int cls[4] = {1, 8, 16, 1 << 20};
     const int q = cls[order_code & 3];
     std::stable_sort(nat.begin(), nat.end(), [q](const WholeItem &a, const WholeItem &b) { return (a.t + q - 1) / q > (b.t + q - 1) / q; });
     const int32_t nit = int32_t(nat.size()), padded = int32_t((nit + RT - 1) / RT) * RT;
-    const int nw = TG / 32, CH = seq ? 32 : 32 * NF;
+    const int nw = TG / 32, CH = 32 * NF;
     for (int32_t r0 = 0; r0 < padded; r0 += RT) {
         // chunks of CH items (longest first); warp w runs on SM sub-partition w % 4
         const int nch = RT / CH;
@@ -372,10 +372,9 @@ int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool mod
             const int tt = (tm + 1) & ~1;
             wgt[c] = 0.5 * tt * (tt + 1);
         }
-        // a warp's unit of work: one chunk, or (seq) the LONG chunk c together with the SHORT chunk nch - 1 - c -- the
-        // work of an item is quadratic in its length, so the sums come out nearly equal
+        // a warp's unit of work: one chunk
         std::vector<double> unit(nw, 0.0);
-        for (int c = 0; c < nw; ++c) unit[c] = seq ? wgt[c] + wgt[nch - 1 - c] : wgt[c];
+        for (int c = 0; c < nw; ++c) unit[c] = wgt[c];
         std::vector<int> warp_of(nw);  // unit -> warp
         // start: SNAKE order over the four sub-partitions (0 1 2 3 / 3 2 1 0 / ...): equal sums of work
         for (int c = 0; c < nw; ++c) { const int grp = c >> 2; warp_of[c] = grp * 4 + ((grp & 1) ? 3 - (c & 3) : (c & 3)); }
@@ -418,7 +417,7 @@ int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool mod
             // side by side: lane l of the warp owns items l and 32 + l of its chunk (neighbours in the length order)
             const int f = slot / TG, tid = slot % TG;
             const int u = unit_of[tid >> 5];
-            const int32_t src = seq ? r0 + (f == 0 ? u : nch - 1 - u) * 32 + (tid & 31) : r0 + u * CH + f * 32 + (tid & 31);
+            const int32_t src = r0 + u * CH + f * 32 + (tid & 31);
             out.push_back(src < nit ? nat[src].w : 0u);
         }
     }
@@ -430,16 +429,13 @@ int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool mod
 void HostIndex::build_whole(int threads, int order, int fibres) {
     whole = WholeHost();
     WholeHost &W = whole;
-    if (m < 2 || m > 3 || N >= 65536 || max_line > kMaxRegT || (threads != 384 && threads != 768) || fibres < 1 || fibres > 3) return;
+    if (m < 2 || m > 3 || N >= 65536 || max_line > kMaxRegT || (threads != 384 && threads != 768) || fibres < 1 || fibres > 2) return;
     for (int h = 1; h < m; ++h)
         if (dims[h].max_lines > kMaxRegT) return;
-    // fibres: 1, 2 (two items of the same length class per thread, folded side by side) or 3 (two items per thread folded
-    // one after the other: a long and a short one)
-    const bool seq = fibres == 3;
+    // fibres: 1 or 2 (two items of the same length class per thread, folded side by side)
     const int TG = threads, NF = fibres == 1 ? 1 : 2, RT = TG * NF;  // a round = RT items: thread i owns slots i, TG + i, ...
     W.threads = threads;
     W.fibres = NF;
-    W.seq = seq;
     auto rounds = [&](int64_t items) { return int32_t((items + RT - 1) / RT) * RT; };
     // seo: per coordinate h >= 1 the line offsets in fibre order; every fibre's list starts on a multiple of four entries
     // (8 bytes: the kernel fetches four offsets per load) and the table ends with a full row of padding (the kernel reads
@@ -478,7 +474,7 @@ void HostIndex::build_whole(int threads, int order, int fibres) {
         const int32_t nit = int32_t(nat.size());
         for (const WholeItem &it : nat) W.max_t = std::max(W.max_t, it.t);
         W.item_off[h] = int32_t(W.items.size());
-        W.n_items[h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, NF, seq, W.items);
+        W.n_items[h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, NF, W.items);
         W.max_items = std::max(W.max_items, nit);
     }
     W.ok = true;
@@ -582,7 +578,7 @@ void HostIndex::build_whole_split(int C, int order) {
             }
             for (const WholeItem &it : nat) W.max_t = std::max(W.max_t, it.t);
             W.item_off[p][h] = int32_t(W.items.size());
-            W.n_items[p][h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, 1, false, W.items);
+            W.n_items[p][h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, 1, W.items);
         }
     }
     for (int q = 0; q < kMaxRegT + 8 || W.seo.size() % 8; ++q) W.seo.push_back(0);

@@ -61,7 +61,6 @@ struct WholeHost {
     bool ok = false;
     int threads = 0;                       // threads per CTA the lists were laid out for (384 or 768)
     int fibres = 1;                        // items per thread and round
-    bool seq = false;                      // two items per thread: false = folded side by side, true = one after the other
     int32_t item_off[3] = {0, 0, 0}, n_items[3] = {0, 0, 0};
     int32_t max_t = 0, max_items = 0;
     std::vector<uint32_t> items;

@@ -44,22 +44,24 @@ cudaError_t whole_launch(const WholeArgs &a, const PackedTri<T> &M, int grid, si
 template <int MODE, bool FMA, int ROWS>
 cudaError_t whole_launch_tg(int threads, bool timeline, const WholeArgs &a, const PackedTri<T> &M, int grid, size_t smem, bool set_attr, cudaStream_t s) {
 #if LPFNT_MAXT == 32
-    if (timeline && MODE == kLowerMatvec)
-        return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS, 1, false, 2, true>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS, 1, false, 1, true>(a, M, grid, smem, set_attr, s);
+    if constexpr (MODE == kLowerMatvec)
+        if (timeline)
+            return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS, 1, false, 2, true>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS, 1, false, 1, true>(a, M, grid, smem, set_attr, s);
 #endif
     return threads == 384 ? whole_launch<MODE, FMA, 384, ROWS, 1, false, 2>(a, M, grid, smem, set_attr, s) : whole_launch<MODE, FMA, 768, ROWS>(a, M, grid, smem, set_attr, s);
 }
-// two fibres per thread, 384 threads, one CTA per SM: side by side (lower mat-vec) or one after the other (any mode)
+// two fibres per thread, 384 threads, one CTA per SM, side by side (lower mat-vec)
 template <int MODE, bool FMA, bool SEQ>
 cudaError_t whole_launch_two(bool timeline, const WholeArgs &a, const PackedTri<T> &M, int grid, size_t smem, bool set_attr, cudaStream_t s) {
 #if LPFNT_MAXT == 32
-    if (timeline && MODE == kLowerMatvec) return whole_launch<MODE, FMA, 384, 2, 2, SEQ, 1, true>(a, M, grid, smem, set_attr, s);
+    if constexpr (MODE == kLowerMatvec)
+        if (timeline) return whole_launch<MODE, FMA, 384, 2, 2, SEQ, 1, true>(a, M, grid, smem, set_attr, s);
 #endif
     return whole_launch<MODE, FMA, 384, 2, 2, SEQ, 1>(a, M, grid, smem, set_attr, s);
 }
 }  // namespace
 
-// fibres: 1; 2 = two per thread side by side; 3 = two per thread one after the other
+// fibres: 1; 2 = two per thread side by side
 template <>
 cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibres, bool timeline, const WholeArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s) {
     PackedTri<T> M;
@@ -74,9 +76,11 @@ cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibre
         if (mode == kLowerMatvec && fibres == 1 && threads == 768 && !timeline)
             return fma ? whole_launch<kLowerMatvec, true, 768, 2, 1, false, 1, false, true>(a, M, grid, smem, set_attr, s)
                        : whole_launch<kLowerMatvec, false, 768, 2, 1, false, 1, false, true>(a, M, grid, smem, set_attr, s);
+#if LPFNT_MAXT == 24
         if (mode == kLowerMatvec && fibres == 1 && threads == 384 && !timeline)
             return fma ? whole_launch<kLowerMatvec, true, 384, 2, 1, false, 2, false, true>(a, M, grid, smem, set_attr, s)
                        : whole_launch<kLowerMatvec, false, 384, 2, 1, false, 2, false, true>(a, M, grid, smem, set_attr, s);
+#endif
 #endif
         if (std::getenv("LPFNT_DEBUG_OCCUPANCY")) std::fprintf(stderr, "launch_whole<%d>: no push variant for mode %d fma %d threads %d fibres %d timeline %d\n", T, mode, int(fma), threads, fibres, int(timeline));
         return cudaErrorNotSupported;
@@ -85,11 +89,7 @@ cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibre
         if (mode != kLowerMatvec || threads != 384) return cudaErrorInvalidValue;
         return fma ? whole_launch_two<kLowerMatvec, true, false>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, false>(timeline, a, M, grid, smem, set_attr, s);
     }
-    if (fibres == 3) {
-        if (threads != 384) return cudaErrorInvalidValue;
-        if (mode != kLowerMatvec) return cudaErrorInvalidValue;  // a measured alternative, kept for the lower mat-vec only
-        return fma ? whole_launch_two<kLowerMatvec, true, true>(timeline, a, M, grid, smem, set_attr, s) : whole_launch_two<kLowerMatvec, false, true>(timeline, a, M, grid, smem, set_attr, s);
-    }
+    if (fibres != 1) return cudaErrorInvalidValue;  // (two fibres one after the other -- "fibres 3" -- lost to both other forms and was removed)
     (void)rows;  // every mode folds two rows side by side (four-row blocks lost to the two-fibre forms and were removed)
     switch (mode) {
         case kLowerMatvec:
@@ -102,7 +102,7 @@ cudaError_t launch_whole<T>(int mode, bool fma, int threads, int rows, int fibre
 
 template <>
 cudaError_t launch_whole_split<T>(bool fma, bool timeline, const WholeSplitArgs &a, const double *tri, int grid, size_t smem, bool set_attr, cudaStream_t s) {
-#if LPFNT_MAXT >= 24
+#if LPFNT_MAXT == 32
     PackedTri<T> M;
     std::memcpy(M.v, tri, sizeof(M.v));
     auto go = [&](auto kern) -> cudaError_t {
@@ -121,7 +121,7 @@ cudaError_t launch_whole_split<T>(bool fma, bool timeline, const WholeSplitArgs 
         kern<<<grid, kSplitThreads, smem, s>>>(a, M);
         return cudaGetLastError();
     };
-#if LPFNT_MAXT == 32
+#ifdef LPFNT_TIMELINE_SPLIT  // development build (LPFNT_TIMELINE_SPLIT=1 python -m lpfun_b200._build): phase stamps, tools/timeline.py
     if (timeline) return fma ? go(k_whole_split<T, true, true>) : go(k_whole_split<T, false, true>);
 #endif
     (void)timeline;

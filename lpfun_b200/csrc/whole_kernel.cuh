@@ -89,6 +89,13 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 __device__ __forceinline__ void multimem_st_f64(double *mc_addr, double v) {
     asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc_addr), "d"(v) : "memory");
 }
+// one result element into every rank's copy; NOT inlined: the store code of k_whole is unrolled over every row of a fibre, and
+// the per-peer loop at each of those sites made the PUSH instantiations 30 % of the library's code
+static __device__ __noinline__ void whole_push_store(double *mc_out, double *const *peer_out, int n_peers, int64_t o, double v) {
+    if (mc_out) multimem_st_f64(mc_out + o, v);
+    else
+        for (int r = 0; r < n_peers; ++r) peer_out[r][o] = v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr unsigned kBulkPiece = 32768;  // bytes per bulk-copy instruction
@@ -294,9 +301,7 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
                         auto put = [&](unsigned idx, double v) {
                             if constexpr (PUSH) {
                                 const int64_t o = int64_t(b) * N + idx;
-                                if (a.mc_out) multimem_st_f64(a.mc_out + o, v);
-                                else
-                                    for (int r = 0; r < a.n_peers; ++r) a.peer_out[r][o] = v;
+                                whole_push_store(a.mc_out, a.peer_out, a.n_peers, o, v);
                             } else {
                                 out[idx] = v;
                             }

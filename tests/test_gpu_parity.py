@@ -417,8 +417,6 @@ def test_eval_few_points_split_path(T, m, n, p, P):
     {"use_whole": 1, "whole_split": 1},
     {"use_whole": 1, "whole_split": 1, "whole_split_c": 7},
     {"use_whole": 1, "whole_split": 1, "whole_split_order": 64},
-    {"use_whole": 1, "whole_fibres": 3},
-    {"use_whole": 1, "whole_fibres": 3, "whole_order": 0},
     {"use_whole": 1, "whole_threads": 768, "whole_fibres": 1},
     {"use_whole": 0, "use_slab": 2},
     {"use_whole": 0, "use_slab": 0},

@@ -1,13 +1,7 @@
-for nl in 2 4; do
-export LPFNT_DEBUG_EVAL_NL=$nl
-echo "NL=$nl"
-python tools/quick_eval.py 4 20 1e7
-python tools/quick_eval.py 3 30 1e7
-python tools/quick_eval.py 6 12 1e6
-python tools/quick_eval.py 4 20 1e7 chebyshev
-python tools/quick_eval.py 2 14 1e7
-done
-unset LPFNT_DEBUG_EVAL_NL
-python tools/overlap.py
-LPFNT_DEBUG_PUSH_CTAS=2 python tools/overlap.py
-python -m pytest tests -m gpu -x -q -k "eval" 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench_pruned.json 2> gpurun_out/bench_pruned.err; tail -c 400 gpurun_out/bench_pruned.err
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/bench_pruned.json') if l.startswith('{')][-1])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d.get('so_MB'), d.get('plan_device_MB'), d.get('plan_build_s'))
+"

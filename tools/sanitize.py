@@ -39,7 +39,6 @@ def check(name, opts, reps):
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 check("d3n12_p1", {"use_whole": 1}, reps)                                   # k_whole, odd N, two CTAs per SM
 check("d3n12_p1", {"use_whole": 1, "whole_fibres": 2}, reps)                # two fibres side by side
-check("d3n12_p1", {"use_whole": 1, "whole_fibres": 3}, reps)                # two fibres one after the other
 check("c2_d3n20_leja", {"use_whole": 1}, reps)                              # colex gather / scatter
 check("c2_d3n20_leja", {"use_whole": 0, "use_slab": 2}, 8)                  # k_slab + k_sweep_groups
 check("d4n8", {"use_whole": 0}, 4)

@@ -2,7 +2,8 @@
 """Phase timeline of the whole-function kernel (k_whole), CTAs 0 and 1, first four functions of each (development helper).
 Stamps per function: 0 top, 1 data in; per coordinate h: 2+4h fibre loaded (last coordinate: + barrier, prefetch issued),
 3+4h triangle code done, 4+4h stored, 5+4h barrier passed (not after the last coordinate).
-   python tools/timeline.py [n] [option=value ...]"""
+   python tools/timeline.py [n] [option=value ...]
+(whole_split=1 needs a library built with LPFNT_TIMELINE_SPLIT=1: the stamped split kernel is not in the default build)"""
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
