@@ -61,6 +61,7 @@ struct lpfnt_plan {
     int32_t *d_line_order = nullptr;
     uint8_t *d_line_alpha = nullptr;
     int2 *d_eval_line = nullptr;
+    int2 *d_eval_tline = nullptr;   // k_eval_tree line descriptors (Newton eval, n < 32)
     int4 *d_eval_block = nullptr;
     double *d_cpad = nullptr;       // padded coefficient layout of the eval kernel
     int32_t num_eval_blocks = 0;
@@ -943,6 +944,7 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         static_assert(sizeof(EvalBlock) == sizeof(int4), "EvalBlock must match int4");
         if ((rc = upload(&p->d_eval_line, reinterpret_cast<const int2 *>(hx.eval_line.data()), hx.eval_line.size(), p))) return fail(rc);
         if ((rc = upload(&p->d_eval_block, reinterpret_cast<const int4 *>(hx.eval_block.data()), hx.eval_block.size(), p))) return fail(rc);
+        if (!hx.eval_tline.empty() && (rc = upload(&p->d_eval_tline, reinterpret_cast<const int2 *>(hx.eval_tline.data()), hx.eval_tline.size(), p))) return fail(rc);
         p->num_eval_blocks = int32_t(hx.eval_block.size());
         p->eval_padded = hx.eval_padded;
     }
@@ -1021,7 +1023,7 @@ int lpfnt_push_rows_ce(int device, const void *src, int64_t bytes, int n_dst, vo
 int lpfnt_plan_destroy(lpfnt_plan *p) {
     if (!p) return LPFNT_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_eval_line); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
+    cudaFree(p->d_eval_line); cudaFree(p->d_eval_tline); cudaFree(p->d_eval_block); cudaFree(p->d_cpad);
     for (auto &es : p->eval_splits) { cudaFree(es.d_l0); cudaFree(es.d_alpha); }
     free_whole(p, 0);
     free_whole(p, 1);
@@ -1362,7 +1364,7 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
             const int64_t np = std::min(step, P - q0);
             cudaError_t e;
             if (blocked) {
-                EvalBlockArgs a{p->d_cpad, dp + q0 * p->m, dv + q0, p->d_eval_block, p->d_eval_line, p->d_line_alpha, np, p->num_eval_blocks, p->m};
+                EvalBlockArgs a{p->d_cpad, dp + q0 * p->m, dv + q0, p->d_eval_block, p->d_eval_line, p->d_eval_tline, p->d_line_alpha, np, p->num_eval_blocks, p->m};
                 trace_begin(p, 1200, s);
                 e = launch_eval_block(a, p->nodes.data(), p->n + 1, p->chebyshev_eval != 0, s);
             } else {

@@ -1,4 +1,5 @@
 // Instantiations + launchers of the point-evaluation kernels and the FP64 probe.
+#include <cstdlib>
 #include <cstring>
 
 #define LPFNT_EVAL_TU 1
@@ -45,7 +46,30 @@ cudaError_t eval_block_launch(const EvalBlockArgs &a, const double *nodes, int n
 }
 }  // namespace
 
+namespace {
+template <int MAXT, int PPT, int MINB>
+cudaError_t eval_tree_launch(const EvalBlockArgs &a, const double *nodes, int n1, cudaStream_t s) {
+    NodeTable<MAXT> nt;
+    for (int k = 0; k < MAXT; ++k) nt.v[k] = (k < n1) ? nodes[k] : 0.0;
+    const int64_t per_block = int64_t(kEvalThreads) * PPT;
+    const int64_t blocks = (a.num_points + per_block - 1) / per_block;
+    if (a.m == 1) k_eval_tree<MAXT, PPT, 1, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else if (a.m <= 4) k_eval_tree<MAXT, PPT, 4, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else if (a.m <= 8) k_eval_tree<MAXT, PPT, 8, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else k_eval_tree<MAXT, PPT, kEvalMaxM, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n1, bool chebyshev, cudaStream_t s) {
+    static const int tree = [] { const char *v = std::getenv("LPFNT_DEBUG_EVAL_TREE"); return v ? atoi(v) : 1; }();
+    if (!chebyshev && tree && a.tlines) {
+        if (n1 <= 8) return eval_tree_launch<8, 2, 3>(a, nodes, n1, s);
+        if (n1 <= 16) return eval_tree_launch<16, 2, 3>(a, nodes, n1, s);
+        if (n1 <= 24) return eval_tree_launch<24, 2, 3>(a, nodes, n1, s);
+        if (n1 <= 32) return tree == 2 ? eval_tree_launch<32, 2, 2>(a, nodes, n1, s) : eval_tree_launch<32, 1, 4>(a, nodes, n1, s);
+        return cudaErrorInvalidValue;
+    }
     if (chebyshev) {
         if (n1 <= 8) return eval_block_launch<8, 2, true>(a, nodes, n1, s);
         if (n1 <= 16) return eval_block_launch<16, 2, true>(a, nodes, n1, s);

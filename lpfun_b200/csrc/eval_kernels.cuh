@@ -125,6 +125,7 @@ struct EvalBlockArgs {
     double *values;            // P
     const int4 *blocks;        // {first line, #lines, padded offset, padded size}
     const int2 *lines;         // {padded offset, t}
+    const int2 *tlines;        // k_eval_tree: {byte offset in the staged block, steps | 8 a_1 << 8 | depth << 16}
     const uint8_t *line_alpha; // N_1 x (m-1)
     int64_t num_points;
     int32_t num_blocks;
@@ -342,6 +343,152 @@ __global__ void __launch_bounds__(THREADS, MAXT > 24 ? 4 : 1) k_eval_block(const
         if constexpr (CHEB) {
             if (m > 1) v = res[q];
         }
+        if (p0 + q < a.num_points) a.values[p0 + q] = v;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Newton evaluation, round 2: same staging and the same nested Horner (every line's chain is unchanged, so the values are those
+// of k_eval_block bit for bit), rebuilt around the instruction count.  ncu of k_eval_block (profiles/r1_k_eval_block_*): 72 % of
+// the issued instructions were not the coefficient FMAs -- per line ~56 instructions of length tests (one compare + branch per
+// four coefficients and line), descriptor / alpha look-ups and a fold loop over all m levels with carry flags -- against 2 x 11
+// FMAs, at 45 % issue utilisation on three warps per sub-partition.  Here
+//   * ONE line at a time, entered through a jump table on ceil(t / 4) (a switch that falls through the unrolled chain): no
+//     per-step tests;
+//   * the descriptor carries a_1 and the fold depth: level 1 is folded with one indexed constant load, and only a line with
+//     a_1 = 0 (one per group of lines) walks the upper levels;
+//   * the next step's coefficients are fetched before the current step's FMAs.
+// ---------------------------------------------------------------------------------------
+template <int MAXT, int PPT, int MM, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_eval_tree(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
+    __shared__ __align__(16) double scb[2][kEvalCB];
+    __shared__ int2 sln[2][kEvalLB];
+    __shared__ __align__(4) uint8_t sal[2][kEvalLB * (MM - 1) + 4];
+    const int tid = threadIdx.x;
+    const int m = a.m;
+    const int64_t p0 = (int64_t(blockIdx.x) * THREADS + tid) * PPT;
+    double x[PPT][MM], d0[PPT][MAXT], acc[PPT][MM];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int64_t p = min(p0 + q, a.num_points - 1);
+#pragma unroll
+        for (int j = 0; j < MM; ++j) {
+            x[q][j] = (j < m) ? a.points[p * m + j] : 0.0;
+            acc[q][j] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
+    }
+
+    auto issue = [&](int bi) {  // stage block bi into buffer bi & 1
+        const int4 b = a.blocks[bi];
+        const int s = bi & 1;
+        for (int i = tid; 2 * i < b.w; i += THREADS) cp_async16_e(&scb[s][2 * i], a.cpad + b.z + 2 * i);
+        for (int i = tid; i < b.y; i += THREADS) cp_async8_e(&sln[s][i], a.tlines + b.x + i);
+        if (m > 2) {  // alpha bytes (only the lines with a_1 = 0 read them): 4-byte words from an aligned start
+            const int64_t a0 = int64_t(b.x) * (m - 1);
+            const int shift = int(a0 & 3);
+            const int nbytes = b.y * (m - 1) + shift;
+            const uint8_t *src = a.line_alpha + (a0 - shift);
+            for (int i = tid; 4 * i < nbytes; i += THREADS) cp_async1_e(&sal[s][4 * i], src + 4 * i, 0);
+        }
+        asm volatile("cp.async.commit_group;" ::);
+    };
+
+    issue(a.num_blocks - 1);
+    for (int bi = a.num_blocks - 1; bi >= 0; --bi) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();  // block bi landed; everybody is done with the buffer block bi-1 goes into
+        if (bi > 0) issue(bi - 1);
+        const int4 b = a.blocks[bi];
+        const int s = bi & 1;
+        const int shift = int((int64_t(b.x) * (m - 1)) & 3);
+        const uint8_t *al_base = &sal[s][shift];
+        const char *cbase = reinterpret_cast<const char *>(&scb[s][0]);
+        int2 ln = sln[s][b.y - 1];
+        for (int li = b.y - 1; li >= 0; --li) {
+            // descriptor: x = byte offset of the line in the staged block; y = steps | 8 a_1 << 8 | depth << 16
+            const int steps = ln.y & 255, a1x8 = (ln.y >> 8) & 255, depth = ln.y >> 16;
+            const double *c = reinterpret_cast<const double *>(cbase + ln.x);
+            if (li > 0) ln = sln[s][li - 1];  // next line's descriptor: in flight during this line
+            double sl[PPT];
+#pragma unroll
+            for (int q = 0; q < PPT; ++q) sl[q] = 0.0;
+            // two coefficient register sets used in turn (even / odd steps): the next step's coefficients are fetched before
+            // the current step's FMAs without register moves; every entry of the jump table fetches its own first step
+            double2 A01, A23, B01, B23;
+#define LPFNT_EVAL_LOAD(KB, C01, C23)                                                                \
+    if constexpr ((KB) < MAXT) {                                                                     \
+        C01 = *reinterpret_cast<const double2 *>(c + (KB));                                          \
+        C23 = *reinterpret_cast<const double2 *>(c + (KB) + 2);                                      \
+    }
+#define LPFNT_EVAL_STEP(KB, C01, C23, N01, N23)                                                      \
+    if constexpr ((KB) < MAXT) {                                                                     \
+        if constexpr ((KB) > 0) {                                                                    \
+            N01 = *reinterpret_cast<const double2 *>(c + (KB) - 4);                                  \
+            N23 = *reinterpret_cast<const double2 *>(c + (KB) - 2);                                  \
+        }                                                                                            \
+        _Pragma("unroll") for (int q = 0; q < PPT; ++q) {                                            \
+            sl[q] = __fma_rn(sl[q], d0[q][(KB) + 3 < MAXT ? (KB) + 3 : 0], C23.y);                   \
+            sl[q] = __fma_rn(sl[q], d0[q][(KB) + 2 < MAXT ? (KB) + 2 : 0], C23.x);                   \
+            sl[q] = __fma_rn(sl[q], d0[q][(KB) + 1 < MAXT ? (KB) + 1 : 0], C01.y);                   \
+            sl[q] = __fma_rn(sl[q], d0[q][(KB) < MAXT ? (KB) : 0], C01.x);                           \
+        }                                                                                            \
+    }
+            switch (steps) {
+                case 8: LPFNT_EVAL_LOAD(28, B01, B23) goto step7;
+                case 7: LPFNT_EVAL_LOAD(24, A01, A23) goto step6;
+                case 6: LPFNT_EVAL_LOAD(20, B01, B23) goto step5;
+                case 5: LPFNT_EVAL_LOAD(16, A01, A23) goto step4;
+                case 4: LPFNT_EVAL_LOAD(12, B01, B23) goto step3;
+                case 3: LPFNT_EVAL_LOAD(8, A01, A23) goto step2;
+                case 2: LPFNT_EVAL_LOAD(4, B01, B23) goto step1;
+                default: LPFNT_EVAL_LOAD(0, A01, A23) goto step0;
+            }
+        step7: LPFNT_EVAL_STEP(28, B01, B23, A01, A23)
+        step6: LPFNT_EVAL_STEP(24, A01, A23, B01, B23)
+        step5: LPFNT_EVAL_STEP(20, B01, B23, A01, A23)
+        step4: LPFNT_EVAL_STEP(16, A01, A23, B01, B23)
+        step3: LPFNT_EVAL_STEP(12, B01, B23, A01, A23)
+        step2: LPFNT_EVAL_STEP(8, A01, A23, B01, B23)
+        step1: LPFNT_EVAL_STEP(4, B01, B23, A01, A23)
+        step0: LPFNT_EVAL_STEP(0, A01, A23, B01, B23)
+#undef LPFNT_EVAL_STEP
+#undef LPFNT_EVAL_LOAD
+            if constexpr (MM == 1) {  // m = 1 (dispatched to this instantiation): the single line is the value
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) acc[q][0] = sl[q];
+            } else {
+                const double nd1 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(nodes.v) + a1x8);
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) acc[q][1] = __fma_rn(acc[q][1], x[q][1] - nd1, sl[q]);
+                if (depth > 0) {  // a_1 = 0: level 1 is complete and goes up, with every further level that completes
+                    const uint8_t *al = al_base + li * (m - 1);
+                    bool carry = true;
+#pragma unroll
+                    for (int j = 2; j < MM; ++j) {
+                        if (j < m && carry) {
+                            const int aj = al[j - 1];
+                            const double nd = nodes.v[aj];
+#pragma unroll
+                            for (int q = 0; q < PPT; ++q) {
+                                acc[q][j] = __fma_rn(acc[q][j], x[q][j] - nd, acc[q][j - 1]);
+                                acc[q][j - 1] = 0.0;
+                            }
+                            carry = (aj == 0);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        double v = acc[q][0];
+#pragma unroll
+        for (int j = 1; j < MM; ++j)
+            if (j == m - 1) v = acc[q][j];
         if (p0 + q < a.num_points) a.values[p0 + q] = v;
     }
 }

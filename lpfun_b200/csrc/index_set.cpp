@@ -338,6 +338,21 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         for (int64_t l = 0; l < N1; ++l)
             for (int j = 1; j < m; ++j) line_alpha[l * (m - 1) + (j - 1)] = static_cast<uint8_t>(key(l, j));
     }
+    // k_eval_tree descriptors: x = byte offset of the line inside its staged block, y = ceil(t / 4) | 8 a_1 << 8 | depth << 16 with
+    // depth = number of levels the line completes (leading zeros of (a_1, a_2, ..)): the common case -- fold into level 1
+    // only -- needs no alpha look-up
+    eval_tline.clear();
+    if (n < 32 && !eval_line.empty()) {
+        eval_tline.resize(N1);
+        for (const EvalBlock &b : eval_block)
+            for (int64_t l = b.l0; l < int64_t(b.l0) + b.nl; ++l) {
+                const int32_t t = line_off[l + 1] - line_off[l];
+                int depth = 0;
+                while (depth < m - 1 && key(l, 1 + depth) == 0) ++depth;
+                const int32_t a1 = m >= 2 ? int32_t(key(l, 1)) : 0;
+                eval_tline[l] = SortedItem{(eval_line[l].x - b.poff) * 8, ((t + 3) >> 2) | (a1 * 8) << 8 | depth << 16};
+            }
+    }
     // ---- last coordinate of every line + the item tables of the whole-function kernel ----
     line_last.clear();
     whole = WholeHost();

@@ -92,6 +92,7 @@ struct HostIndex {
     WholeSplitHost wsplit;
     std::vector<int32_t> line_order;     // N_1: lines ordered by length inside every chunk of kLineChunk
     std::vector<SortedItem> eval_line;   // N_1: {padded coefficient offset, line length}
+    std::vector<SortedItem> eval_tline;  // N_1: k_eval_tree descriptors {byte offset in the staged block, steps | 8 a_1 << 8 | depth << 16}
     std::vector<EvalBlock> eval_block;   // blocks of lines staged together by the eval kernel
     int64_t eval_padded = 0;             // size of the padded coefficient layout (doubles)
     std::vector<uint8_t> line_alpha;     // N_1 * (m-1): (a_1..a_{m-1}) of every line, for eval (n <= 255)
