@@ -61,15 +61,9 @@ cudaError_t eval_tree_launch(const EvalBlockArgs &a, const double *nodes, int n1
 }
 }  // namespace
 
+// Newton basis: k_eval_tree; Chebyshev basis: k_eval_block<.., CHEB = true> (the Newton instantiations of k_eval_block were
+// dropped from the library when k_eval_tree replaced them: same values bit for bit, 122 -> 91 ms at config 5)
 cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n1, bool chebyshev, cudaStream_t s) {
-    static const int tree = [] { const char *v = std::getenv("LPFNT_DEBUG_EVAL_TREE"); return v ? atoi(v) : 1; }();
-    if (!chebyshev && tree && a.tlines) {
-        if (n1 <= 8) return eval_tree_launch<8, 2, 3>(a, nodes, n1, s);
-        if (n1 <= 16) return eval_tree_launch<16, 2, 3>(a, nodes, n1, s);
-        if (n1 <= 24) return eval_tree_launch<24, 2, 3>(a, nodes, n1, s);
-        if (n1 <= 32) return tree == 2 ? eval_tree_launch<32, 2, 2>(a, nodes, n1, s) : eval_tree_launch<32, 1, 4>(a, nodes, n1, s);
-        return cudaErrorInvalidValue;
-    }
     if (chebyshev) {
         if (n1 <= 8) return eval_block_launch<8, 2, true>(a, nodes, n1, s);
         if (n1 <= 16) return eval_block_launch<16, 2, true>(a, nodes, n1, s);
@@ -77,10 +71,11 @@ cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n
         if (n1 <= 32) return eval_block_launch<32, 1, true>(a, nodes, n1, s);
         return cudaErrorInvalidValue;
     }
-    if (n1 <= 8) return eval_block_launch<8, 2, false>(a, nodes, n1, s);
-    if (n1 <= 16) return eval_block_launch<16, 2, false>(a, nodes, n1, s);
-    if (n1 <= 24) return eval_block_launch<24, 2, false>(a, nodes, n1, s);
-    if (n1 <= 32) return eval_block_launch<32, 1, false>(a, nodes, n1, s);
+    if (!a.tlines) return cudaErrorInvalidValue;
+    if (n1 <= 8) return eval_tree_launch<8, 2, 3>(a, nodes, n1, s);
+    if (n1 <= 16) return eval_tree_launch<16, 2, 3>(a, nodes, n1, s);
+    if (n1 <= 24) return eval_tree_launch<24, 2, 3>(a, nodes, n1, s);
+    if (n1 <= 32) return eval_tree_launch<32, 1, 4>(a, nodes, n1, s);  // (two points per thread at 198 registers: no faster)
     return cudaErrorInvalidValue;
 }
 
