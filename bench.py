@@ -307,7 +307,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-LABEL_NAMES = {0: "k_sweep_lines", 1: "k_sweep_groups", 2: "k_sweep_generic", 3: "k_eval_horner", 8: "k_permute", 11: "k_eval_pad", 12: "k_eval_block", 14: "k_whole", 16: "k_slab"}
+LABEL_NAMES = {0: "k_sweep_lines", 1: "k_sweep_groups", 2: "k_sweep_generic", 3: "k_eval_horner", 8: "k_permute", 11: "k_eval_pad", 12: "k_eval_tree", 14: "k_whole", 16: "k_slab"}
 
 
 def summarize_trace(recs):

@@ -1345,7 +1345,7 @@ int lpfnt_newton2point(lpfnt_plan *p, const double *coeffs, const double *points
     }
     if (split_done) {
     } else if (fast) {
-        const bool blocked = p->use_eval_block && p->d_eval_block && p->eval_padded > 0 && (p->m == 1 || p->d_line_alpha) && (p->chebyshev_eval || p->d_eval_tline);
+        const bool blocked = p->use_eval_block && p->d_eval_block && p->eval_padded > 0 && (p->m == 1 || p->d_line_alpha) && p->d_eval_tline;
         if (blocked && !p->d_cpad) {
             if (cudaMalloc(reinterpret_cast<void **>(&p->d_cpad), sizeof(double) * size_t(p->eval_padded + 4)) != cudaSuccess) { set_error("cudaMalloc(cpad) failed"); return LPFNT_ENOMEM; }
             p->table_bytes += int64_t(sizeof(double)) * (p->eval_padded + 4);

@@ -33,45 +33,30 @@ cudaError_t launch_eval_horner(const EvalArgs &a, const double *nodes, int n1, c
 }
 
 namespace {
-template <int MAXT, int PPT, bool CHEB>
-cudaError_t eval_block_launch(const EvalBlockArgs &a, const double *nodes, int n1, cudaStream_t s) {
-    NodeTable<MAXT> nt;
-    for (int k = 0; k < MAXT; ++k) nt.v[k] = (k < n1) ? nodes[k] : 0.0;
-    const int64_t per_block = int64_t(kEvalThreads) * PPT;
-    const int64_t blocks = (a.num_points + per_block - 1) / per_block;
-    if (a.m <= 4) k_eval_block<MAXT, PPT, 4, kEvalThreads, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else if (a.m <= 8) k_eval_block<MAXT, PPT, 8, kEvalThreads, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else k_eval_block<MAXT, PPT, kEvalMaxM, kEvalThreads, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    return cudaGetLastError();
-}
-}  // namespace
-
-namespace {
-template <int MAXT, int PPT, int MINB>
+template <int MAXT, int PPT, int MINB, bool CHEB = false>
 cudaError_t eval_tree_launch(const EvalBlockArgs &a, const double *nodes, int n1, cudaStream_t s) {
     NodeTable<MAXT> nt;
     for (int k = 0; k < MAXT; ++k) nt.v[k] = (k < n1) ? nodes[k] : 0.0;
     const int64_t per_block = int64_t(kEvalThreads) * PPT;
     const int64_t blocks = (a.num_points + per_block - 1) / per_block;
-    if (a.m == 1) k_eval_tree<MAXT, PPT, 1, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else if (a.m <= 4) k_eval_tree<MAXT, PPT, 4, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else if (a.m <= 8) k_eval_tree<MAXT, PPT, 8, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
-    else k_eval_tree<MAXT, PPT, kEvalMaxM, kEvalThreads, MINB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    if (a.m == 1) k_eval_tree<MAXT, PPT, 1, kEvalThreads, MINB, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else if (a.m <= 4) k_eval_tree<MAXT, PPT, 4, kEvalThreads, MINB, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else if (a.m <= 8) k_eval_tree<MAXT, PPT, 8, kEvalThreads, MINB, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
+    else k_eval_tree<MAXT, PPT, kEvalMaxM, kEvalThreads, MINB, CHEB><<<unsigned(blocks), kEvalThreads, 0, s>>>(a, nt);
     return cudaGetLastError();
 }
 }  // namespace
 
-// Newton basis: k_eval_tree; Chebyshev basis: k_eval_block<.., CHEB = true> (the Newton instantiations of k_eval_block were
-// dropped from the library when k_eval_tree replaced them: same values bit for bit, 122 -> 91 ms at config 5)
+// many points, Newton or Chebyshev basis: k_eval_tree on the padded, block-staged coefficients
 cudaError_t launch_eval_block(const EvalBlockArgs &a, const double *nodes, int n1, bool chebyshev, cudaStream_t s) {
+    if (!a.tlines) return cudaErrorInvalidValue;
     if (chebyshev) {
-        if (n1 <= 8) return eval_block_launch<8, 2, true>(a, nodes, n1, s);
-        if (n1 <= 16) return eval_block_launch<16, 2, true>(a, nodes, n1, s);
-        if (n1 <= 24) return eval_block_launch<24, 2, true>(a, nodes, n1, s);
-        if (n1 <= 32) return eval_block_launch<32, 1, true>(a, nodes, n1, s);
+        if (n1 <= 8) return eval_tree_launch<8, 2, 3, true>(a, nodes, n1, s);
+        if (n1 <= 16) return eval_tree_launch<16, 2, 3, true>(a, nodes, n1, s);
+        if (n1 <= 24) return eval_tree_launch<24, 2, 3, true>(a, nodes, n1, s);  // (204 registers / two CTAs per SM: 120 vs 113 ms)
+        if (n1 <= 32) return eval_tree_launch<32, 1, 4, true>(a, nodes, n1, s);
         return cudaErrorInvalidValue;
     }
-    if (!a.tlines) return cudaErrorInvalidValue;
     if (n1 <= 8) return eval_tree_launch<8, 2, 3>(a, nodes, n1, s);
     if (n1 <= 16) return eval_tree_launch<16, 2, 3>(a, nodes, n1, s);
     if (n1 <= 24) return eval_tree_launch<24, 2, 3>(a, nodes, n1, s);

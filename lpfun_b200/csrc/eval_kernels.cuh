@@ -109,15 +109,14 @@ __global__ void __launch_bounds__(THREADS) k_eval_horner(const EvalArgs a, const
 }
 
 // ---------------------------------------------------------------------------------------
-// Block-staged evaluation (the fast path).  Same nested Horner as k_eval_horner, restructured
-// after ncu showed it latency bound at ~10 % of the FP64 pipe (8 warps/SM at 212 registers, one
-// dependent chain descriptor -> coefficients -> FMA chain -> fold per line):
+// Block-staged evaluation (the fast path): shared staging of k_eval_tree below.
 //   * the coefficients are first re-laid out with every line padded to a multiple of 4 doubles
 //     (k_eval_pad; zero filled), so a line is a run of aligned 32-byte groups;
 //   * a CTA stages blocks of <= 256 lines (<= 24 KB of padded coefficients + descriptors) in shared
 //     memory with cp.async, double buffered: no global latency on the critical path;
-//   * every thread owns PPT points and runs TWO lines at a time (2 x PPT independent FMA chains);
-//     coefficients come from shared memory as 16-byte broadcasts (one LDS per two coefficients).
+//   * coefficients come from shared memory as 16-byte broadcasts (one LDS per two coefficients).
+// (Round 1's kernel on this staging, k_eval_block -- two lines at a time, a length test per four coefficients -- was replaced
+// by k_eval_tree in round 2 and removed: 122 -> 91 ms Newton, 202 -> 113 ms Chebyshev at d = 4, n = 20, 10^7 points.)
 // ---------------------------------------------------------------------------------------
 struct EvalBlockArgs {
     const double *cpad;        // padded coefficients
@@ -168,199 +167,24 @@ __device__ __forceinline__ void cp_async1_e(void *smem_dst, const void *gsrc, in
     (void)bytes4;
 }
 
+// ---------------------------------------------------------------------------------------
+// Evaluation, round 2: the nested Horner over the index trie rebuilt around the instruction count.  ncu of round 1's kernel
+// (profiles/r1_k_eval_block_*): 72 % of the issued instructions were not the coefficient FMAs -- per line ~56 instructions of
+// length tests (one compare + branch per four coefficients and line), descriptor / alpha look-ups and a fold loop over all m
+// levels with carry flags -- against 2 x 11 FMAs, at 45 % issue utilisation on three warps per sub-partition.  Here
+//   * ONE line at a time, entered through a jump table on ceil(t / 4) into a chain that falls through: no per-step tests;
+//   * the descriptor carries a_1 and the fold depth: level 1 is folded with one indexed constant load, and only a line with
+//     a_1 = 0 (one per group of lines) walks the upper levels;
+//   * the next step's coefficients are fetched before the current step's FMAs (two register sets used in turn).
+// Every line's chain is the one round 1 ran, so the values are unchanged bit for bit.
 // CHEB = true evaluates in the Chebyshev basis (chebyshev2point, src/lpfun/utils.py:165-195) with the same trie walk:
 //   * coordinate 0: d0[q][k] holds T_k(x_0) (three-term recurrence, as the reference builds its basis table) and a
 //     line is the dot product sum_k c_k T_k(x_0) (the zero padding contributes nothing);
 //   * coordinates j >= 1: the lines are visited with a_j DEscending, so sum_{a_j} T_{a_j}(x_j) * below_{a_j} is a
 //     Clenshaw recurrence b = below + 2 x_j b1 - b2 with two running values per level; at a_j = 0 the level's value
 //     is b - x_j b1 and the state resets.
-// Capacity 32 (one point per thread) runs at 128 registers / 4 CTAs per SM (measured 5122 vs 4680 Gpair/s at d=3, n=30);
-// the two-point variants keep their 162 registers (forcing 128 costs them a third: 3134 vs 4707 Gpair/s at d=4, n=20).
-template <int MAXT, int PPT, int MM, int THREADS, bool CHEB = false>
-__global__ void __launch_bounds__(THREADS, MAXT > 24 ? 4 : 1) k_eval_block(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
-    __shared__ __align__(16) double scb[2][kEvalCB];
-    __shared__ int2 sln[2][kEvalLB];
-    __shared__ __align__(4) uint8_t sal[2][kEvalLB * (MM - 1) + 4];
-    const int tid = threadIdx.x;
-    const int m = a.m;
-    const int64_t p0 = (int64_t(blockIdx.x) * THREADS + tid) * PPT;
-    double x[PPT][MM], d0[PPT][MAXT], acc[PPT][MM];
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        const int64_t p = min(p0 + q, a.num_points - 1);
-#pragma unroll
-        for (int j = 0; j < MM; ++j) {
-            x[q][j] = (j < m) ? a.points[p * m + j] : 0.0;
-            acc[q][j] = 0.0;
-        }
-        if constexpr (CHEB) {
-            d0[q][0] = 1.0;
-            if (MAXT > 1) d0[q][1] = x[q][0];
-#pragma unroll
-            for (int k = 1; k + 1 < MAXT; ++k) d0[q][k + 1] = __dsub_rn(__dmul_rn(__dmul_rn(2.0, x[q][0]), d0[q][k]), d0[q][k - 1]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
-        }
-    }
-    double b2[CHEB ? PPT : 1][CHEB ? MM : 1];  // Clenshaw: acc[][] holds b_{k+1}, b2[][] holds b_{k+2}
-    double res[PPT];
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) res[q] = 0.0;
-    if constexpr (CHEB) {
-#pragma unroll
-        for (int q = 0; q < PPT; ++q)
-#pragma unroll
-            for (int j = 0; j < MM; ++j) b2[q][j] = 0.0;
-    }
-
-    auto issue = [&](int bi) {  // stage block bi into buffer bi & 1
-        const int4 b = a.blocks[bi];
-        const int s = bi & 1;
-        for (int i = tid; 2 * i < b.w; i += THREADS) cp_async16_e(&scb[s][2 * i], a.cpad + b.z + 2 * i);
-        for (int i = tid; i < b.y; i += THREADS) cp_async8_e(&sln[s][i], a.lines + b.x + i);
-        // alpha bytes of the block's lines: (m-1) bytes per line, copied in 4-byte words (the source
-        // offset b.x*(m-1) is made 4-byte aligned by starting a few bytes early)
-        const int64_t a0 = int64_t(b.x) * (m - 1);
-        const int shift = int(a0 & 3);
-        const int nbytes = b.y * (m - 1) + shift;
-        const uint8_t *src = a.line_alpha + (a0 - shift);
-        for (int i = tid; 4 * i < nbytes; i += THREADS) cp_async1_e(&sal[s][4 * i], src + 4 * i, 0);
-        asm volatile("cp.async.commit_group;" ::);
-    };
-
-    issue(a.num_blocks - 1);
-    for (int bi = a.num_blocks - 1; bi >= 0; --bi) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();  // block bi landed; everybody is done with the buffer block bi-1 goes into
-        if (bi > 0) issue(bi - 1);
-        const int4 b = a.blocks[bi];
-        const int s = bi & 1;
-        const int shift = int((int64_t(b.x) * (m - 1)) & 3);
-        const uint8_t *al_base = &sal[s][shift];
-        for (int li = b.y - 1; li >= 0; li -= 2) {
-            const int2 lA = sln[s][li];
-            const int2 lB = (li > 0) ? sln[s][li - 1] : make_int2(lA.x, 0);
-            const double *cA = &scb[s][lA.x - b.z];
-            const double *cB = &scb[s][lB.x - b.z];
-            const int tA = lA.y, tB = lB.y;
-            double sA[PPT], sB[PPT];
-#pragma unroll
-            for (int q = 0; q < PPT; ++q) sA[q] = sB[q] = 0.0;
-#pragma unroll
-            for (int kb = MAXT - 4; kb >= 0; kb -= 4) {
-                if (kb < tA) {  // zero padding: the partial sum stays 0 until the first real coefficient
-                    const double2 c01 = *reinterpret_cast<const double2 *>(cA + kb);
-                    const double2 c23 = *reinterpret_cast<const double2 *>(cA + kb + 2);
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) {
-                        if constexpr (CHEB) {
-                            sA[q] = __fma_rn(c23.y, d0[q][kb + 3], sA[q]);
-                            sA[q] = __fma_rn(c23.x, d0[q][kb + 2], sA[q]);
-                            sA[q] = __fma_rn(c01.y, d0[q][kb + 1], sA[q]);
-                            sA[q] = __fma_rn(c01.x, d0[q][kb], sA[q]);
-                        } else {
-                            sA[q] = __fma_rn(sA[q], d0[q][kb + 3], c23.y);
-                            sA[q] = __fma_rn(sA[q], d0[q][kb + 2], c23.x);
-                            sA[q] = __fma_rn(sA[q], d0[q][kb + 1], c01.y);
-                            sA[q] = __fma_rn(sA[q], d0[q][kb], c01.x);
-                        }
-                    }
-                }
-                if (kb < tB) {
-                    const double2 c01 = *reinterpret_cast<const double2 *>(cB + kb);
-                    const double2 c23 = *reinterpret_cast<const double2 *>(cB + kb + 2);
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) {
-                        if constexpr (CHEB) {
-                            sB[q] = __fma_rn(c23.y, d0[q][kb + 3], sB[q]);
-                            sB[q] = __fma_rn(c23.x, d0[q][kb + 2], sB[q]);
-                            sB[q] = __fma_rn(c01.y, d0[q][kb + 1], sB[q]);
-                            sB[q] = __fma_rn(c01.x, d0[q][kb], sB[q]);
-                        } else {
-                            sB[q] = __fma_rn(sB[q], d0[q][kb + 3], c23.y);
-                            sB[q] = __fma_rn(sB[q], d0[q][kb + 2], c23.x);
-                            sB[q] = __fma_rn(sB[q], d0[q][kb + 1], c01.y);
-                            sB[q] = __fma_rn(sB[q], d0[q][kb], c01.x);
-                        }
-                    }
-                }
-            }
-            // fold line A, then line B, into level 1 and every level that completes with them
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                if (which == 1 && li == 0) break;
-                const uint8_t *al = al_base + (li - which) * (m - 1);
-                bool carry = true;
-                double val[PPT];  // CHEB: value handed from a completed level to the next one
-#pragma unroll
-                for (int q = 0; q < PPT; ++q) val[q] = 0.0;
-#pragma unroll
-                for (int j = 1; j < MM; ++j) {
-                    if (j < m && carry) {
-                        const int aj = al[j - 1];
-                        if constexpr (CHEB) {
-                            // Clenshaw step of level j with the completed value of level j - 1 (kept in val[q])
-#pragma unroll
-                            for (int q = 0; q < PPT; ++q) {
-                                const double below = (j == 1) ? (which == 0 ? sA[q] : sB[q]) : val[q];
-                                const double b = __fma_rn(2.0 * x[q][j], acc[q][j], below - b2[q][j]);
-                                if (aj == 0) {  // level complete: its value goes up, the state resets
-                                    val[q] = __fma_rn(-x[q][j], acc[q][j], b);
-                                    if (j == m - 1) res[q] = val[q];  // the root: happens once, with the very last line
-                                    acc[q][j] = 0.0;
-                                    b2[q][j] = 0.0;
-                                } else {
-                                    b2[q][j] = acc[q][j];
-                                    acc[q][j] = b;
-                                }
-                            }
-                        } else {
-                            const double nd = nodes.v[aj];
-#pragma unroll
-                            for (int q = 0; q < PPT; ++q) {
-                                const double below = (j == 1) ? (which == 0 ? sA[q] : sB[q]) : acc[q][j - 1];
-                                acc[q][j] = __fma_rn(acc[q][j], x[q][j] - nd, below);
-                                if (j > 1) acc[q][j - 1] = 0.0;
-                            }
-                        }
-                        carry = (aj == 0);
-                    }
-                }
-                if (m == 1) {
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) acc[q][0] = (which == 0) ? sA[q] : sB[q];
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        double v = acc[q][0];
-#pragma unroll
-        for (int j = 1; j < MM; ++j)
-            if (j == m - 1) v = acc[q][j];
-        if constexpr (CHEB) {
-            if (m > 1) v = res[q];
-        }
-        if (p0 + q < a.num_points) a.values[p0 + q] = v;
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------
-// Newton evaluation, round 2: same staging and the same nested Horner (every line's chain is unchanged, so the values are those
-// of k_eval_block bit for bit), rebuilt around the instruction count.  ncu of k_eval_block (profiles/r1_k_eval_block_*): 72 % of
-// the issued instructions were not the coefficient FMAs -- per line ~56 instructions of length tests (one compare + branch per
-// four coefficients and line), descriptor / alpha look-ups and a fold loop over all m levels with carry flags -- against 2 x 11
-// FMAs, at 45 % issue utilisation on three warps per sub-partition.  Here
-//   * ONE line at a time, entered through a jump table on ceil(t / 4) (a switch that falls through the unrolled chain): no
-//     per-step tests;
-//   * the descriptor carries a_1 and the fold depth: level 1 is folded with one indexed constant load, and only a line with
-//     a_1 = 0 (one per group of lines) walks the upper levels;
-//   * the next step's coefficients are fetched before the current step's FMAs.
-// ---------------------------------------------------------------------------------------
-template <int MAXT, int PPT, int MM, int THREADS, int MINB>
+template <int MAXT, int PPT, int MM, int THREADS, int MINB, bool CHEB = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_eval_tree(const EvalBlockArgs a, const __grid_constant__ NodeTable<MAXT> nodes) {
     __shared__ __align__(16) double scb[2][kEvalCB];
     __shared__ int2 sln[2][kEvalLB];
@@ -377,8 +201,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_eval_tree(const EvalBlockArgs
             x[q][j] = (j < m) ? a.points[p * m + j] : 0.0;
             acc[q][j] = 0.0;
         }
+        if constexpr (CHEB) {  // T_k(x_0) by the three-term recurrence, as the reference builds its basis table (utils.py:165-195)
+            d0[q][0] = 1.0;
+            if (MAXT > 1) d0[q][1] = x[q][0];
 #pragma unroll
-        for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
+            for (int k = 1; k + 1 < MAXT; ++k) d0[q][k + 1] = __dsub_rn(__dmul_rn(__dmul_rn(2.0, x[q][0]), d0[q][k]), d0[q][k - 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) d0[q][k] = x[q][0] - nodes.v[k];
+        }
+    }
+    // CHEB: levels j >= 1 are Clenshaw recurrences (the lines come with a_j descending): acc[][] holds b_{k+1}, b2[][] b_{k+2}
+    double b2[CHEB ? PPT : 1][CHEB ? MM : 1], res[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) res[q] = 0.0;
+    if constexpr (CHEB) {
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+#pragma unroll
+            for (int j = 0; j < MM; ++j) b2[q][j] = 0.0;
     }
 
     auto issue = [&](int bi) {  // stage block bi into buffer bi & 1
@@ -430,10 +271,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_eval_tree(const EvalBlockArgs
             N23 = *reinterpret_cast<const double2 *>(c + (KB) - 2);                                  \
         }                                                                                            \
         _Pragma("unroll") for (int q = 0; q < PPT; ++q) {                                            \
-            sl[q] = __fma_rn(sl[q], d0[q][(KB) + 3 < MAXT ? (KB) + 3 : 0], C23.y);                   \
-            sl[q] = __fma_rn(sl[q], d0[q][(KB) + 2 < MAXT ? (KB) + 2 : 0], C23.x);                   \
-            sl[q] = __fma_rn(sl[q], d0[q][(KB) + 1 < MAXT ? (KB) + 1 : 0], C01.y);                   \
-            sl[q] = __fma_rn(sl[q], d0[q][(KB) < MAXT ? (KB) : 0], C01.x);                           \
+            if constexpr (CHEB) {                                                                    \
+                sl[q] = __fma_rn(C23.y, d0[q][(KB) + 3 < MAXT ? (KB) + 3 : 0], sl[q]);               \
+                sl[q] = __fma_rn(C23.x, d0[q][(KB) + 2 < MAXT ? (KB) + 2 : 0], sl[q]);               \
+                sl[q] = __fma_rn(C01.y, d0[q][(KB) + 1 < MAXT ? (KB) + 1 : 0], sl[q]);               \
+                sl[q] = __fma_rn(C01.x, d0[q][(KB) < MAXT ? (KB) : 0], sl[q]);                       \
+            } else {                                                                                 \
+                sl[q] = __fma_rn(sl[q], d0[q][(KB) + 3 < MAXT ? (KB) + 3 : 0], C23.y);               \
+                sl[q] = __fma_rn(sl[q], d0[q][(KB) + 2 < MAXT ? (KB) + 2 : 0], C23.x);               \
+                sl[q] = __fma_rn(sl[q], d0[q][(KB) + 1 < MAXT ? (KB) + 1 : 0], C01.y);               \
+                sl[q] = __fma_rn(sl[q], d0[q][(KB) < MAXT ? (KB) : 0], C01.x);                       \
+            }                                                                                        \
         }                                                                                            \
     }
             switch (steps) {
@@ -459,6 +307,46 @@ __global__ void __launch_bounds__(THREADS, MINB) k_eval_tree(const EvalBlockArgs
             if constexpr (MM == 1) {  // m = 1 (dispatched to this instantiation): the single line is the value
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) acc[q][0] = sl[q];
+            } else if constexpr (CHEB) {
+                // Clenshaw step of level 1 with the line's value; a_1 = 0 (depth > 0) completes the level: its value goes up
+                double bq[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) bq[q] = __fma_rn(2.0 * x[q][1], acc[q][1], sl[q] - b2[q][1]);
+                if (depth == 0) {
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) { b2[q][1] = acc[q][1]; acc[q][1] = bq[q]; }
+                } else {
+                    double val[PPT];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        val[q] = __fma_rn(-x[q][1], acc[q][1], bq[q]);
+                        if (m == 2) res[q] = val[q];
+                        acc[q][1] = 0.0;
+                        b2[q][1] = 0.0;
+                    }
+                    const uint8_t *al = al_base + li * (m - 1);
+                    bool carry = true;
+#pragma unroll
+                    for (int j = 2; j < MM; ++j) {
+                        if (j < m && carry) {
+                            const int aj = al[j - 1];
+#pragma unroll
+                            for (int q = 0; q < PPT; ++q) {
+                                const double b = __fma_rn(2.0 * x[q][j], acc[q][j], val[q] - b2[q][j]);
+                                if (aj == 0) {
+                                    val[q] = __fma_rn(-x[q][j], acc[q][j], b);
+                                    if (j == m - 1) res[q] = val[q];  // the root: once, with the very last line
+                                    acc[q][j] = 0.0;
+                                    b2[q][j] = 0.0;
+                                } else {
+                                    b2[q][j] = acc[q][j];
+                                    acc[q][j] = b;
+                                }
+                            }
+                            carry = (aj == 0);
+                        }
+                    }
+                }
             } else {
                 const double nd1 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(nodes.v) + a1x8);
 #pragma unroll
@@ -489,6 +377,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_eval_tree(const EvalBlockArgs
 #pragma unroll
         for (int j = 1; j < MM; ++j)
             if (j == m - 1) v = acc[q][j];
+        if constexpr (CHEB && MM > 1) v = res[q];
         if (p0 + q < a.num_points) a.values[p0 + q] = v;
     }
 }

@@ -299,7 +299,7 @@ bool HostIndex::build(const int64_t *A, int64_t N_, int m_, int n_) {
         });
     }
 
-    // ---- eval program (k_eval_block): the coefficient vector is re-laid out per call with every line
+    // ---- eval program (k_eval_tree): the coefficient vector is re-laid out per call with every line
     //      padded to a multiple of 4 doubles (32-byte aligned, zero filled), and the lines are cut into
     //      blocks of <= kEvalBlockLines lines / <= kEvalBlockElems padded doubles that a CTA stages in
     //      shared memory.  eval_line = {padded offset, t}; eval_block = {first line, #lines, padded
