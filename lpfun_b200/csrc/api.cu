@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <bitset>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -86,6 +88,7 @@ struct lpfnt_plan {
     // workspaces (grown on demand): two lanes x {staged input, staged output, permutation scratch}
     double *ws[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t ws_bytes[6] = {0, 0, 0, 0, 0, 0};
+    int dbg_uploads = 0;            // LPFNT_DEBUG_BYTES: running number of the table uploads
     cudaStream_t stream = nullptr, stream2 = nullptr;  // used by the host-pointer paths (two lanes)
     // pageable host arrays (the reference's plain NumPy contract) are staged through pinned buffers by several host threads
     double *hstage[4] = {nullptr, nullptr, nullptr, nullptr};  // lane 0 in / out, lane 1 in / out
@@ -151,6 +154,9 @@ int upload(T **dst, const T *src, size_t count, lpfnt_plan *p) {
     CK(cudaMalloc(reinterpret_cast<void **>(dst), count * sizeof(T)));
     CK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
     p->table_bytes += int64_t(count * sizeof(T));
+    static const bool dbg = std::getenv("LPFNT_DEBUG_BYTES") != nullptr;
+    if (dbg && count * sizeof(T) >= (size_t(1) << 20)) std::fprintf(stderr, "lpfnt upload #%d: %.1f MB (tables %.1f MB)\n", ++p->dbg_uploads, count * sizeof(T) / 1e6, p->table_bytes / 1e6);
+    else if (dbg) ++p->dbg_uploads;
     return LPFNT_OK;
 }
 
@@ -938,7 +944,6 @@ int lpfnt_plan_create(int m, int n, int64_t N, const int64_t *A, const int64_t *
         }
         for (int which = 0; which < 2; ++which)
             if ((rc = upload_whole(p, which))) return fail(rc);
-        if ((rc = upload_wsplit(p))) return fail(rc);
     }
     if (!hx.eval_block.empty()) {
         static_assert(sizeof(EvalBlock) == sizeof(int4), "EvalBlock must match int4");
@@ -1084,10 +1089,19 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
     }
     if (std::strcmp(name, "use_whole") == 0) { p->use_whole = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
     if (std::strcmp(name, "whole_split_skew") == 0) { p->whole_split_skew = int(std::max<int64_t>(0, std::min<int64_t>(value, 1000000))); return LPFNT_OK; }
-    if (std::strcmp(name, "whole_split") == 0) { p->use_whole_split = value < 0 ? -1 : (value ? 1 : 0); return LPFNT_OK; }
+    if (std::strcmp(name, "whole_split") == 0) {
+        p->use_whole_split = value < 0 ? -1 : (value ? 1 : 0);
+        if (p->use_whole_split != 0 && !p->wsplit.h.ok) {  // the tables (16 MB of scratch at d = 3, n = 30) are built on first request
+            CK(cudaSetDevice(p->device));
+            CK(cudaDeviceSynchronize());
+            return upload_wsplit(p);
+        }
+        return LPFNT_OK;
+    }
     if (std::strcmp(name, "whole_split_c") == 0 || std::strcmp(name, "whole_split_order") == 0) {
         if (name[12] == 'c') p->whole_split_c = int(std::max<int64_t>(0, std::min<int64_t>(value, 16)));
         else p->whole_split_order = value < 0 ? kWholeDefaultOrder : int(value & 127);
+        if (p->use_whole_split == 0) return LPFNT_OK;  // used when the split kernel is switched on
         CK(cudaSetDevice(p->device));
         CK(cudaDeviceSynchronize());
         return upload_wsplit(p);

@@ -298,12 +298,21 @@ class Transform:
     # ------------------------------------------------------------------ ops
     def warmup(self) -> None:
         """Run every op once on zeros (loads the kernels; mirrors transform.py:415-428)."""
-        z = np.zeros(self._N_0, dtype=np.float64)
+        # on DEVICE arrays: a host array would leave the two staging buffers of the host-pointer path (2 x 8 N bytes) in the
+        # plan for good -- 112 MB at d = 6, n = 20 that a device-resident caller never uses
+        if torch is None:
+            z = np.zeros(self._N_0, dtype=np.float64)
+            self.fnt(z); self.ifnt(z); self.dx(z, 0); self.dxT(z, 0)
+            self.eval(z, np.zeros((1, self._m), dtype=np.float64))
+            return
+        dev = torch.device("cuda", self._device)
+        z = torch.zeros(self._N_0, dtype=torch.float64, device=dev)
         self.fnt(z)
         self.ifnt(z)
         self.dx(z, 0)
         self.dxT(z, 0)
-        self.eval(z, np.zeros((1, self._m), dtype=np.float64))
+        self.eval(z, torch.zeros((1, self._m), dtype=torch.float64, device=dev))
+        torch.cuda.synchronize(dev)
 
     def fnt(self, function_values, out=None):
         """Fast Newton Transform: values on ``grid`` -> Newton coefficients (transform.py:430-551).
