@@ -646,6 +646,30 @@ def test_chebyshev_eval_fast_kernel_vs_oracle(T, m, n, p):
     t.close()
 
 
+@pytest.mark.parametrize("basis", ["newton", "chebyshev"])
+@pytest.mark.parametrize("m,n,p", [(7, 5, 2.0), (9, 3, 2.0), (12, 2, 1.0), (8, 4, np.inf), (3, 31, 2.0), (1, 31, 2.0)])
+def test_eval_tree_kernel_many_levels_and_full_capacity(T, m, n, p, basis):
+    """k_eval_tree at the ends of its template grid: 5..12 coordinates (the instantiations with 8 and 12 fold levels), the
+    full 32-entry node table, a single coordinate; Newton and Chebyshev; the one-thread-per-point path forced (eval_split 0);
+    a point count that is not a multiple of the CTA's 256 points."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(101 * m + n)
+    t = T(m, n, lp_degree=p, basis=basis, report=False)
+    o = O.OracleTransform(m, n, p, basis=basis)
+    c = rng.standard_normal(len(t)) / (1.0 + np.arange(len(t))) ** 0.5
+    pts = rng.uniform(-1, 1, (517, m))
+    want = o.eval(c, pts)
+    t.set_option("eval_split", 0)
+    got = t.eval(c, pts)
+    tol = TOL_EVAL if n < 25 else 1e-10
+    assert relmax(got, want) <= tol
+    if len(t) * m <= (1 << 20):  # (larger sets do not keep the multi-index array the fallback kernel walks)
+        t.set_option("force_generic", 1)
+        assert relmax(t.eval(c, pts), want) <= tol
+    t.close()
+
+
 @pytest.mark.parametrize("n,B", [(25, 1), (25, 16), (28, 9), (29, 300), (12, 7)])
 def test_whole_function_kernel_odd_sizes(T, n, B):
     """k_whole with an odd number of coefficients: every second function starts 8 bytes off the 16-byte grid of the
