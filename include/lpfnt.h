@@ -111,7 +111,8 @@ int lpfnt_index_destroy(lpfnt_index *index);
  * `threads` threads (384 or 768), `fibres` (1 item per thread and round; 2: two of equal length class, folded side by
  * side) and an item order (2 bits per coordinate, 0 strict length order,
  * 1 / 2 classes of 8 / 16 rows, 3 natural; + 64: chunks of 32 items dealt to the warps by a model of the shared FP64 pipe
- * instead of the snake order over the four SM sub-partitions; < 0 = default).  lpfnt_index_whole_meta fills 10 int32: ok, threads,
+ * instead of the snake order over the four SM sub-partitions; + 128: the chunks of coordinate 0 go to the warps in reverse, so
+ * that the warps leaving the previous function's last sweep first start on the long lines; < 0 = default).  lpfnt_index_whole_meta fills 10 int32: ok, threads,
  * longest item, most items of a list, {list offset, padded list length} per coordinate; returns the number written. */
 int lpfnt_index_whole_build(lpfnt_index *index, int threads, int order, int fibres);
 int lpfnt_index_whole_meta(const lpfnt_index *index, int32_t *meta);

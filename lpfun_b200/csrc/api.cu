@@ -1117,7 +1117,7 @@ int lpfnt_plan_set_option(lpfnt_plan *p, const char *name, int64_t value) {
                 lpfnt_plan::WholeCfg &c = p->wcfg[w];
                 if (key == "threads") c.threads = (value == 384 || value == 768) ? int(value) : -1;
                 else if (key == "fibres") c.fibres = (value >= 1 && value <= 2) ? int(value) : -1;
-                else if (key == "order") c.order = value < 0 ? kWholeDefaultOrder : int(value & 127);
+                else if (key == "order") c.order = value < 0 ? kWholeDefaultOrder : int(value & 255);
                 else c.rows = (value == 2 || value == 4) ? int(value) : -1;
             }
             if (key == "rows") return LPFNT_OK;

@@ -370,7 +370,7 @@ struct WholeItem { int t; uint32_t w; };
 // Orders the items of one sweep (length classes, natural order inside a class) and appends them to `out` in THREAD order:
 // rounds of TG * NF slots, thread i owning slots i, TG + i; inside a round chunks of 32 items dealt to the warps.
 // Returns the padded list length.
-int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool model, int TG, int NF, std::vector<uint32_t> &out) {
+int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool model, int TG, int NF, std::vector<uint32_t> &out, bool reverse = false) {
     const int RT = TG * NF;
     const int cls[4] = {1, 8, 16, 1 << 20};
     const int q = cls[order_code & 3];
@@ -426,6 +426,10 @@ int32_t layout_whole_items(std::vector<WholeItem> &nat, int order_code, bool mod
                     }
             }
         }
+        // reverse: the warps that carry the longest items of the other sweeps get the shortest ones here (coordinate 0 follows
+        // the previous function's LAST sweep without a barrier: the warps that leave it first then start on the long items)
+        if (reverse)
+            for (int c = 0; c < nw; ++c) warp_of[c] = nw - 1 - warp_of[c];
         std::vector<int> unit_of(nw);
         for (int c = 0; c < nw; ++c) unit_of[warp_of[c]] = c;
         for (int slot = 0; slot < RT; ++slot) {
@@ -489,7 +493,7 @@ void HostIndex::build_whole(int threads, int order, int fibres) {
         const int32_t nit = int32_t(nat.size());
         for (const WholeItem &it : nat) W.max_t = std::max(W.max_t, it.t);
         W.item_off[h] = int32_t(W.items.size());
-        W.n_items[h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, NF, W.items);
+        W.n_items[h] = layout_whole_items(nat, (order >> (2 * h)) & 3, (order & 64) != 0, TG, NF, W.items, h == 0 && (order & 128) != 0);
         W.max_items = std::max(W.max_items, nit);
     }
     W.ok = true;

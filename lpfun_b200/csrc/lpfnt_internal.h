@@ -105,6 +105,6 @@ struct HostIndex {
     // (re)build `wsplit` (m = 3): C = split plane (<= 0: the one that balances the parts)
     void build_whole_split(int C, int order);
 };
-constexpr int kWholeDefaultOrder = 0 | (2 << 2) | (2 << 4) | 64;
+constexpr int kWholeDefaultOrder = 0 | (2 << 2) | (2 << 4) | 64 | 128;  // + 128: coordinate 0's chunks dealt to the warps in reverse
 
 }  // namespace lpfnt

@@ -66,6 +66,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
     asm volatile(
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
         for (int e = threadIdx.x; e < N; e += TG) W_SPERM[e] = __ldg(a.perm16 + e);
     if (threadIdx.x == 0) {
         mbar_init(W_BAR, 1);
+        mbar_init(W_BAR + 1, TG / 32);  // "every warp has gathered its lines" (one arrival per warp and function)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
         if (gather_cp) issue_gather(blockIdx.x);
         else if (threadIdx.x == 0) issue_bulk(blockIdx.x);
     }
-    unsigned parity = 0;
+    unsigned parity = 0, gparity = 0;
 #pragma unroll 1
     for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
         stamp(0);
@@ -246,7 +250,12 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
 #pragma unroll
                             for (int k = 0; k < MAXT; ++k) x[f][k] = (k < t) ? buf[sp[k]] : 0.0;
                         }
-                        __syncthreads();  // the gather reads other lines' slots: nobody writes before everybody has read
+                        // The gather reads other lines' slots: nobody may write before everybody has read.  As a SPLIT barrier
+                        // (arrive here, wait in front of the stores): a CTA barrier at this place held the warps that finish
+                        // the previous function's last sweep early -- those with the short items -- until the last warp had
+                        // arrived (9 K of 42.6 K cycles per function in the phase timeline).
+                        __syncwarp();
+                        if ((threadIdx.x & 31) == 0) mbar_arrive(W_BAR + 1);
                     } else if (h == 0) {
 #pragma unroll
                         for (int f = 0; f < NF; ++f) {
@@ -334,6 +343,10 @@ __global__ void __launch_bounds__(TG, MINB) k_whole(const __grid_constant__ Whol
                     } else {
                         double *buf = buf0 + ((oddN && !gather_cp) ? (b & 1) : 0);
                         if (h == 0) {
+                            if (f == 0 && a.gather && !gather_cp) {  // every warp has read its lines through the permutation
+                                mbar_wait(W_BAR + 1, gparity);
+                                gparity ^= 1;
+                            }
                             double *q = buf + (it & 0xffffu);
 #pragma unroll
                             for (int k = 0; k < MAXT; ++k)
