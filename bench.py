@@ -483,7 +483,7 @@ def run_c4_strong(args, torch, dist, t, dev, rank, world, K):
                             sl = slice(lo, hi)
                             t.fnt(vals[sl], out=coef[sl]); t.ifnt(coef[sl], out=mine[sl])
                             comm.wait_stream(torch.cuda.current_stream(dev))
-                            pg.push_rows(lo, hi, stream=comm, engine=eng)
+                            pg.push_rows(lo, hi, stream=comm, engine=eng, alone=(hi == Bl))  # no sweep follows the last chunk
                         torch.cuda.current_stream(dev).wait_stream(comm)
                     pg.barrier()
 

@@ -162,6 +162,9 @@ int lpfnt_plan_destroy(lpfnt_plan *plan);
  * mc_dst its multicast mapping (one multimem.st.v4 per 16 bytes reaches every GPU).  Runs on `stream`, so it overlaps the sweeps of
  * the next chunk on another stream. */
 int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, void *stream);
+/* ... with the number of copy CTAs (128 threads) per SM: 1 (what lpfnt_push_rows uses) runs beside the sweep kernels of the next
+ * chunk, more (up to 16) is faster for a copy that no sweep follows (the last chunk of a step) */
+int lpfnt_push_rows_ex(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, int ctas_per_sm, void *stream);
 /* ... and by the copy engines (one cudaMemcpyAsync per peer mapping): no SM is taken from the persistent sweep kernels, so the
  * transfer really runs behind them */
 int lpfnt_push_rows_ce(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *stream);

@@ -53,6 +53,7 @@ def _declare(L):
     L.lpfnt_plan_destroy.argtypes = [vp]
     L.lpfnt_plan_set_push.argtypes = [vp, vp, i64, i32, C.POINTER(vp), vp]
     L.lpfnt_push_rows.argtypes = [i32, vp, i64, i32, C.POINTER(vp), vp, vp]
+    L.lpfnt_push_rows_ex.argtypes = [i32, vp, i64, i32, C.POINTER(vp), vp, i32, vp]
     L.lpfnt_push_rows_ce.argtypes = [i32, vp, i64, i32, C.POINTER(vp), vp]
     L.lpfnt_plan_device_bytes.restype = i64
     L.lpfnt_plan_device_bytes.argtypes = [vp]

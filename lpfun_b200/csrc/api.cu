@@ -988,7 +988,7 @@ int lpfnt_plan_set_push(lpfnt_plan *p, const void *local_base, int64_t bytes, in
     return LPFNT_OK;
 }
 
-int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, void *stream) {
+int lpfnt_push_rows_ex(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, int ctas_per_sm, void *stream) {
     if (!src || bytes <= 0 || (bytes & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || n_dst < 0 || n_dst > 8 || (n_dst > 0 && !dst) || (n_dst == 0 && !mc_dst)) {
         set_error("push_rows: need a 16-byte aligned source, a multiple of 16 bytes and 1..8 destinations or a multicast mapping");
         return LPFNT_EINVAL;
@@ -1005,13 +1005,18 @@ int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void 
     if (!a.mc && a.n_dst == 0) return LPFNT_OK;
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 148;  // (cudaGetDeviceProperties takes milliseconds)
-    // ONE small CTA per SM: it fits beside the persistent sweep CTA (4096 registers are left); two would keep the next sweep
-    // CTA out of the SM until the copy has finished
-    static const int per_sm = [] { const char *v = std::getenv("LPFNT_DEBUG_PUSH_CTAS"); return v ? std::max(1, atoi(v)) : 1; }();
+    // ctas_per_sm = 1 (lpfnt_push_rows): ONE small CTA per SM fits beside the persistent sweep CTA (4096 registers are left); two
+    // would keep the next sweep CTA out of the SM until the copy has finished.  A copy that nothing follows (the last chunk of
+    // a step) takes more: 8 CTAs per SM move 436 MB to seven peers in 0.60 instead of 0.69 ms.
+    const int per_sm = std::max(1, std::min(ctas_per_sm, 16));
     const int grid = int(std::min<int64_t>((a.words + 127) / 128, int64_t(sms) * per_sm));
     cudaError_t e = launch_push_rows(a, grid, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { set_error(std::string("push_rows launch: ") + cudaGetErrorString(e)); return LPFNT_ECUDA; }
     return LPFNT_OK;
+}
+
+int lpfnt_push_rows(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *mc_dst, void *stream) {
+    return lpfnt_push_rows_ex(device, src, bytes, n_dst, dst, mc_dst, 1, stream);
 }
 
 int lpfnt_push_rows_ce(int device, const void *src, int64_t bytes, int n_dst, void *const *dst, void *stream) {

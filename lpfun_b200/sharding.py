@@ -153,10 +153,11 @@ class PushGather:
         """This rank's rows of the full result (pass as ``out=``)."""
         return self.full[self._a:self._b]
 
-    def push_rows(self, lo: int, hi: int, stream=None, engine: str = "sm"):
+    def push_rows(self, lo: int, hi: int, stream=None, engine: str = "sm", alone: bool = False):
         """Send the rows [lo, hi) of THIS rank's block (already written into its own copy) to every other rank's copy:
-        engine="sm" a streaming copy kernel (multimem.st.v4 when the buffer has a multicast mapping), engine="ce" the copy
-        engines (they need no SM, so the transfer overlaps the persistent sweep kernels)."""
+        engine="sm" a streaming copy kernel (multimem.st.v4 when the buffer has a multicast mapping; one small CTA per SM
+        beside the sweep kernels, eight when ``alone`` says that no sweep follows), engine="ce" the copy engines (they need
+        no SM)."""
         import ctypes as C
 
         from . import _native as nat
@@ -184,8 +185,9 @@ class PushGather:
                 s.wait_stream(self._peer_streams[(self.rank + q) % self.world])
             return
         mc = C.c_void_p(self._mc_base + first) if self._mc_base else C.c_void_p(0)
-        nat.check(nat.lib().lpfnt_push_rows(self.t.device, C.c_void_p(self._peer_bases[self.rank] + first), nbytes,
-                                            0 if self._mc_base else self.world, dst, mc, C.c_void_p(s.cuda_stream)))
+        nat.check(nat.lib().lpfnt_push_rows_ex(self.t.device, C.c_void_p(self._peer_bases[self.rank] + first), nbytes,
+                                               0 if self._mc_base else self.world, dst, mc, 8 if alone else 1,
+                                               C.c_void_p(s.cuda_stream)))
 
     def barrier(self):
         """Every rank's stores have landed everywhere (device-side barrier on the current stream)."""

@@ -33,7 +33,7 @@ def copy(stream):
     if engine == "ce":
         nat.check(nat.lib().lpfnt_push_rows_ce(0, C.c_void_p(src.data_ptr()), src.numel() * 8, 1, one, C.c_void_p(stream.cuda_stream)))
     else:
-        nat.check(nat.lib().lpfnt_push_rows(0, C.c_void_p(src.data_ptr()), src.numel() * 8, 1, one, C.c_void_p(0), C.c_void_p(stream.cuda_stream)))
+        nat.check(nat.lib().lpfnt_push_rows_ex(0, C.c_void_p(src.data_ptr()), src.numel() * 8, 1, one, C.c_void_p(0), int(os.environ.get('CTAS', 1)), C.c_void_p(stream.cuda_stream)))
 
 
 def timed(f, K=10):
@@ -63,5 +63,5 @@ b = timed(lambda: copy(torch.cuda.current_stream(dev)))
 c = timed(lambda: both(True))
 d = timed(lambda: both(False))
 assert torch.equal(src, dst)
-print(f"engine {engine} B={B} CB={CB} ctas/SM={os.environ.get('LPFNT_DEBUG_PUSH_CTAS','1')} carveout={os.environ.get('LPFNT_DEBUG_PUSH_CARVEOUT','-')}: "
+print(f"engine {engine} B={B} CB={CB} ctas/SM={os.environ.get('CTAS','1')} carveout={os.environ.get('LPFNT_DEBUG_PUSH_CARVEOUT','-')}: "
       f"sweeps {a:.3f} ms, copy {b:.3f} ms ({src.numel()*8/b/1e6:.0f} GB/s), both(copy launched first) {c:.3f} ms, both(sweeps first) {d:.3f} ms")
