@@ -646,6 +646,40 @@ def test_chebyshev_eval_fast_kernel_vs_oracle(T, m, n, p):
     t.close()
 
 
+def test_device_calls_are_cuda_graph_capturable(T):
+    """Device-pointer calls only enqueue on the caller's stream and allocate nothing once the plan is warm: a loop of dx /
+    fnt / ifnt calls can be captured in a CUDA graph (launch-bound loops: 6.8 instead of 23 us per dx at d=4, n=20) and
+    the replay reproduces the eager results bit for bit."""
+    import torch
+
+    t = T(4, 9, report=False)
+    rng = np.random.default_rng(5)
+    c = torch.as_tensor(rng.standard_normal(len(t)), device="cuda")
+    d = [torch.empty_like(c) for _ in range(4)]
+    v = torch.empty_like(c); r = torch.empty_like(c)
+    for i in range(4):
+        t.dx(c, i, 1, out=d[i])
+    t.ifnt(c, out=v); t.fnt(v, out=r)
+    torch.cuda.synchronize()
+    want = [x.clone() for x in d] + [v.clone(), r.clone()]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(4):
+            t.dx(c, i, 1, out=d[i])
+        t.ifnt(c, out=v); t.fnt(v, out=r)
+    for x in d + [v, r]:
+        x.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for got, w in zip(d + [v, r], want):
+        assert torch.equal(got, w)
+    c.mul_(2.0)  # the graph reads the buffers it was captured on
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(d[0], 2.0 * want[0])
+    t.close()
+
+
 @pytest.mark.parametrize("basis", ["newton", "chebyshev"])
 @pytest.mark.parametrize("m,n,p", [(7, 5, 2.0), (9, 3, 2.0), (12, 2, 1.0), (8, 4, np.inf), (3, 31, 2.0), (1, 31, 2.0)])
 def test_eval_tree_kernel_many_levels_and_full_capacity(T, m, n, p, basis):
