@@ -1,1 +1,3 @@
-python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 --sweep whole_order=192,208,224,196,212,228,200,216,232,193,209,225,197,213,229,201,217,233,194,210,226,198,214,230,202,218,234,168,40 2>&1 | grep whole_order
+python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 2>&1 | tail -1
+python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 --opt whole_threads_exact=384 --opt whole_fibres_exact=2 2>&1 | tail -1
+python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 --opt whole_threads_fma=768 --opt whole_fibres_fma=1 2>&1 | tail -1
