@@ -255,9 +255,10 @@ class Transform:
         if _is_cuda_tensor(v):
             if v.device.index != self._device:
                 raise ValueError(f"{what}: tensor lives on cuda:{v.device.index}, the plan on cuda:{self._device}")
-            t = v.to(torch.float64).contiguous()
+            # (a launch-bound caller -- dx in a loop, 7 us of kernel -- pays for every tensor op here: convert only when needed)
+            t = v if (v.dtype is torch.float64 and v.is_contiguous()) else v.to(torch.float64).contiguous()
             squeeze = t.dim() == 1
-            t = t.reshape(1, -1) if squeeze else t
+            t = t.unsqueeze(0) if squeeze else t
             if t.dim() != 2 or t.shape[1] != self._N_0:
                 raise ValueError(f"{what}: expected shape ({self._N_0},) or (B, {self._N_0}), got {tuple(v.shape)}")
             return t, True, squeeze
@@ -287,12 +288,14 @@ class Transform:
                 ok = ok and out.flags["C_CONTIGUOUS"] and out.size == x.size
             if not ok:
                 raise ValueError("out= must be a contiguous float64 array of the input's shape on the same side (host/device)")
-            return out.reshape(x.shape)
+            return out if out.shape == x.shape else out.reshape(x.shape)
         if on_device:
             return torch.empty_like(x)
         return np.empty_like(x)
 
-    def _finish(self, out, squeeze: bool):
+    def _finish(self, out, squeeze: bool, user_out=None):
+        if user_out is not None and (user_out.ndim == 1) == squeeze:
+            return user_out  # the caller's own array (same memory as `out`)
         return out[0] if squeeze else out
 
     # ------------------------------------------------------------------ ops
@@ -319,17 +322,19 @@ class Transform:
 
         Bit-identical to the reference (same operation order, unfused multiply/add)."""
         x, dev, sq = self._vec_in(function_values, "fnt")
+        user_out = out
         out = self._out_like(x, dev, out)
         nat.check(nat.lib().lpfnt_fnt(self._plan, self._ptr(x), self._ptr(out), x.shape[0], int(dev), self._stream(dev)))
-        return self._finish(out, sq)
+        return self._finish(out, sq, user_out)
 
     def ifnt(self, coefficients, out=None):
         """Inverse transform: coefficients -> values on ``grid`` (transform.py:553-632)."""
         x, dev, sq = self._vec_in(coefficients, "ifnt")
+        user_out = out
         out = self._out_like(x, dev, out)
         arith = nat.ARITH_EXACT if self._exact_ifnt else nat.ARITH_FMA
         nat.check(nat.lib().lpfnt_ifnt(self._plan, self._ptr(x), self._ptr(out), x.shape[0], arith, int(dev), self._stream(dev)))
-        return self._finish(out, sq)
+        return self._finish(out, sq, user_out)
 
     def _check_ik(self, i, k):
         i, k = int(i), int(k)
@@ -343,17 +348,19 @@ class Transform:
         """k-th partial derivative along coordinate i, in coefficient space (transform.py:634-718)."""
         i, k = self._check_ik(i, k)
         x, dev, sq = self._vec_in(coefficients, "dx")
+        user_out = out
         out = self._out_like(x, dev, out)
         nat.check(nat.lib().lpfnt_dx(self._plan, self._ptr(x), self._ptr(out), i, k, x.shape[0], int(dev), self._stream(dev)))
-        return self._finish(out, sq)
+        return self._finish(out, sq, user_out)
 
     def dxT(self, coefficients, i: int, k: Literal[1, 2, 3] = 1, out=None):
         """Adjoint of :meth:`dx` (transform.py:720-804)."""
         i, k = self._check_ik(i, k)
         x, dev, sq = self._vec_in(coefficients, "dxT")
+        user_out = out
         out = self._out_like(x, dev, out)
         nat.check(nat.lib().lpfnt_dxT(self._plan, self._ptr(x), self._ptr(out), i, k, x.shape[0], int(dev), self._stream(dev)))
-        return self._finish(out, sq)
+        return self._finish(out, sq, user_out)
 
     def eval(self, coefficients, points):
         """Evaluate the expansion at arbitrary points, shape (P, m) -> (P,) (transform.py:806-848)."""
