@@ -1,3 +1,4 @@
-python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 2>&1 | tail -1
-python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 --opt whole_threads_exact=384 --opt whole_fibres_exact=2 2>&1 | tail -1
-python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 --check 0 --opt whole_threads_fma=768 --opt whole_fibres_fma=1 2>&1 | tail -1
+python -m pytest tests -m gpu -x -q -k "whole or golden or push or odd or shapes" 2>&1 | tail -2
+python tools/quick.py --m 3 --n 30 --batch 4096 --iters 10 2>&1 | tail -3
+python tools/quick.py --m 3 --n 20 --batch 8192 --iters 10 2>&1 | tail -2
+python tools/quick.py --m 2 --n 30 --batch 16384 --iters 10 2>&1 | tail -2
